@@ -1,0 +1,180 @@
+/*
+ * zc_b200.h -- C-ABI of libzc_b200.so, the B200-native batched MCTS engine.
+ *
+ * This is the drop-in boundary for ONE hot path of rishabhgoel0213/ZeroClone:
+ *     Engine.play_mcts / play_mcts_parallel   (engine/engine.py:119-138)
+ *       -> engine.mcts.get_move               (engine/mcts/src/mcts.cpp:102-160,
+ *                                              bound at engine/mcts/src/bindings_mcts.cpp:9-11)
+ *       -> backend.get_legal_moves/play_move  (engine/games/chess/src/bindings_chess.cpp:44-57,
+ *                                              engine/games/connect4/c4_backend.py:11-61)
+ *       -> Value.batch                        (engine/value_functions.py:16-32)
+ * In the reference these are pybind11 modules called once per tree and once per simulation;
+ * here one handle owns thousands of trees in HBM and one call advances all of them.
+ * INTEGRATION.md shows the ctypes binding a reference maintainer would add.
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative ZC_E* code; zc_last_error() gives text;
+ *     nothing throws across the ABI; no torch types anywhere;
+ *   - "host" pointers are ordinary (preferably pinned) memory, "dev" pointers are device memory
+ *     on the handle's device (e.g. torch.Tensor.data_ptr());
+ *   - `stream` is a cudaStream_t passed as void* (NULL = the legacy default stream); all device
+ *     work of a call is enqueued on it, host-buffer variants synchronise that stream before
+ *     returning;
+ *   - no CPU fallback exists: without a CUDA device every entry point that computes returns
+ *     ZC_ENODEVICE.
+ */
+#ifndef ZC_B200_H
+#define ZC_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ZC_ABI_VERSION 1
+
+/* error codes */
+#define ZC_OK 0
+#define ZC_EINVAL (-1)    /* bad argument                                        */
+#define ZC_ENODEVICE (-2) /* no usable CUDA device                               */
+#define ZC_ECUDA (-3)     /* a CUDA call failed, see zc_last_error()             */
+#define ZC_ECAPACITY (-4) /* a tree outgrew its node arena (raise arena_slots)   */
+#define ZC_ESTATE (-5)    /* call sequence violated (e.g. backprop before select) */
+
+/* games: engine/games/<game>/ in the reference */
+#define ZC_GAME_C4 0
+#define ZC_GAME_CHESS 1
+
+/* leaf evaluators (engine/value_functions.py) */
+#define ZC_EVAL_C4_TERMINAL 0   /* -1 if check_win(state) else 0 : terminal branch of random_rollout, :41-43   */
+#define ZC_EVAL_C4_POSITIONAL 1 /* -1 on a win, else sum_discs w[col]*(+1 side to move / -1 opponent) / 64       */
+#define ZC_EVAL_CHESS_CRUDE 2   /* crude_chess_score, :49-55                                                   */
+#define ZC_EVAL_EXTERNAL 3      /* values supplied by the caller per batch (the neural evaluator, :61-129)     */
+#define ZC_EVAL_C4_ROLLOUT 4    /* random_rollout, :35-45, device RNG (throughput only, not bit-reproducible)   */
+
+/* expansion policies (engine/policy_functions.py; mcts.cpp:65-78 takes any callable) */
+#define ZC_POLICY_FIRST 0  /* policy(moves) = moves[0]  : deterministic, used for parity                        */
+#define ZC_POLICY_LAST 1   /* policy(moves) = moves[-1] : deterministic, used for parity                        */
+#define ZC_POLICY_RANDOM 2 /* Policy.random, :10-12 : uniform among untried moves, device RNG                   */
+
+/* ---- packed root states ---------------------------------------------------------------- */
+
+/* Connect Four (c4_backend.py:4 State(board, turn)).  Cell (row r, column c), row 0 = top,
+ * is bit  c*7 + (5-r)  ; bit c*7+6 is always 0.  x = discs of 'X' (turn 0), o = discs of 'O'. */
+typedef struct zc_c4_state {
+    uint64_t x;
+    uint64_t o;
+    int32_t turn;
+    int32_t reserved;
+} zc_c4_state;
+
+/* Chess (include/state.h:9-23 without the two history deques, which only check_draw reads).
+ * board[r*8+c], row 0 = rank 8, ASCII piece letters, ' ' or 0 = empty. */
+typedef struct zc_chess_state {
+    uint8_t board[64];
+    uint8_t turn; /* 0 = white */
+    uint8_t fifty_move_rule_counter;
+    uint8_t w_ck, w_cq, b_ck, b_cq;
+    uint8_t reserved[2];
+} zc_chess_state;
+
+/* a chess move as the reference prints it: ((fr,fc,tr,tc), value) -- chess_backend.cpp:52-64 */
+typedef struct zc_chess_move {
+    uint8_t fr, fc, tr, tc;
+    float value; /* captured piece value 0/1/3/5/9 */
+} zc_chess_move;
+
+#define ZC_MAX_MOVES 256 /* >= 218, the chess maximum; C4 uses 7 */
+
+/* per-tree result of a search: what get_move returns (mcts.cpp:150-159) plus the statistics the
+ * reference computes but does not expose */
+typedef struct zc_root_result {
+    int32_t n_moves;            /* legal moves at the root, in backend order                */
+    int32_t best;               /* index of the chosen move, -1 if no child was visited     */
+    int32_t root_visits;        /* root N                                                   */
+    int32_t status;             /* 0, or ZC_ECAPACITY for this tree                         */
+    uint8_t best_move[4];       /* chess fr,fc,tr,tc ; C4 col,0,0,0                         */
+    float best_move_value;      /* chess capture value of the chosen move                   */
+    int32_t nodes;              /* nodes in the tree                                        */
+    int64_t sum_leaf_depth;     /* sum over simulations of the evaluated leaf's depth       */
+    int32_t max_leaf_depth;
+    int32_t reevaluated_leaves; /* simulations that re-evaluated a move-less node           */
+} zc_root_result;
+
+typedef struct zc_search zc_search; /* opaque: node arenas + control blocks of up to max_trees trees */
+
+/* ---- library ----------------------------------------------------------------------------- */
+int zc_abi_version(void);
+const char *zc_last_error(void);
+int zc_device_count(void);
+
+/* CPython set-iteration order of C4 moves (c4_backend.py:49-50 returns a set): table[mask][i] is
+ * the i-th column for the playable-column bit mask, 255-terminated.  A CPython 3.12 table is
+ * built in; the Python host re-derives it from the running interpreter at import. */
+int zc_c4_set_move_order(const uint8_t *table /* [128][8] */);
+int zc_c4_get_move_order(uint8_t *table /* [128][8] */);
+
+/* ---- search handle: replaces get_move() for a whole batch of trees ----------------------- */
+
+/* arena_slots_per_tree: 16-byte slots per tree, 0 = default (C4: exact worst case;
+ * chess: (max_sims+1) * 48).  Memory = max_trees * arena_slots_per_tree * 16 B. */
+int zc_search_create(int game, int device, int max_trees, int max_sims, int64_t arena_slots_per_tree,
+                     zc_search **out);
+int zc_search_destroy(zc_search *h);
+int64_t zc_search_device_bytes(const zc_search *h);
+
+/* Upload n root states (host memory) and build the root nodes (backend.get_legal_moves(root),
+ * mcts.cpp:104-109).  states: zc_c4_state[n] or zc_chess_state[n] according to the game. */
+int zc_search_set_roots(zc_search *h, const void *host_states, int n, void *stream);
+/* same, states already in device memory */
+int zc_search_set_roots_dev(zc_search *h, const void *dev_states, int n, void *stream);
+
+/* The whole of get_move's simulation loop (mcts.cpp:129-149) for all trees with a built-in
+ * evaluator, in one persistent kernel: `simulations` sims per tree, frozen-statistics batches of
+ * `batch_size` (1..32, the reference default is 32), UCB1 constant c.  Asynchronous on stream. */
+int zc_search_run(zc_search *h, int simulations, double c, int batch_size, int evaluator, int policy,
+                  uint64_t seed, void *stream);
+
+/* The same loop cut at the evaluator for ZC_EVAL_EXTERNAL (value.batch, mcts.cpp:112-127):
+ *   zc_search_begin(...)
+ *   while (zc_search_pending(h) > 0) {
+ *       zc_search_select(h, planes, ...)      // select + expand one batch per tree, pack leaves
+ *       values = network(planes)              // caller (PyTorch)
+ *       zc_search_backprop(h, values, ...)    // backprop in pending order
+ *   }
+ * Leaf i of tree t is row t*batch_size+i of `dev_planes` / `dev_values`. */
+int zc_search_begin(zc_search *h, int simulations, double c, int batch_size, int policy, uint64_t seed);
+int zc_search_pending(const zc_search *h); /* simulations per tree still to run */
+/* dev_planes: [n_trees*batch_size][C][H][W] (C4: 2x6x7, c4_backend.py:52-61; chess: 17x8x8,
+ * chess_backend.cpp:461-521), plane_dtype 0 = bf16, 1 = f32, 2 = f16.  Rows of batches shorter
+ * than batch_size (the last batch) are zero-filled. */
+int zc_search_select(zc_search *h, void *dev_planes, int plane_dtype, void *stream);
+int zc_search_backprop(zc_search *h, const float *dev_values, void *stream);
+
+/* Root readout: chosen move (mcts.cpp:150-155: most-visited child, lowest index on ties) and
+ * per-child Na / Wa.  results: zc_root_result[n]; visits: int32[n][stride]; value_sums:
+ * double[n][stride]; moves: zc_chess_move[n][stride] (C4: fr = column); the last three may be
+ * NULL.  Host buffers; synchronises stream. */
+int zc_search_results(zc_search *h, zc_root_result *results, int32_t *visits, double *value_sums,
+                      zc_chess_move *moves, int stride, void *stream);
+
+/* Order-dependent 64-bit hash over every node and edge of each tree (same function as
+ * oracle/zc_oracle.c:hash_tree): equality means the whole tree matches the reference's bit for bit. */
+int zc_search_tree_hash(zc_search *h, uint64_t *host_hashes, void *stream);
+
+/* counters for roofline accounting, summed over trees since the last set_roots */
+typedef struct zc_search_counters {
+    int64_t simulations;
+    int64_t nodes;
+    int64_t sum_leaf_depth;
+    int64_t sum_path_children; /* sum over descent steps of the children scanned */
+    int64_t arena_slots_used;
+    int64_t kernel_launches;   /* kernels launched by this handle since creation */
+} zc_search_counters;
+int zc_search_get_counters(zc_search *h, zc_search_counters *out, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ZC_B200_H */

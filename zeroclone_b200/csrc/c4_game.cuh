@@ -1,0 +1,78 @@
+// Connect Four plugged into the generic search (search.cuh).
+#pragma once
+#include "c4_rules.cuh"
+#include "search.cuh"
+#include "../../include/zc_b200.h"
+
+namespace zc {
+
+struct C4Game {
+    using State = c4::State;
+    static constexpr int SS = 1;            // state slots per node
+    static constexpr int FIRST_SLOTS = 9;   // header + state + up to 7 edges: the whole node in one warp load
+    static constexpr int PLANE_ELEMS = 84;  // 2 x 6 x 7 (c4_backend.py:52-61)
+
+    ZC_D static State state_from_lanes(const uint4& v) {
+        const uint4 s = shfl4(v, 1);
+        State st;
+        st.cur = ((uint64_t)s.y << 32) | s.x;
+        st.opp = ((uint64_t)s.w << 32) | s.z;
+        return st;
+    }
+    ZC_HD static void store_state(uint4* dst, const State& s) {
+        *dst = make_uint4((uint32_t)s.cur, (uint32_t)(s.cur >> 32), (uint32_t)s.opp, (uint32_t)(s.opp >> 32));
+    }
+    ZC_HD static State load_state(const uint4* src) {
+        const uint4 s = *src;
+        State st;
+        st.cur = ((uint64_t)s.y << 32) | s.x;
+        st.opp = ((uint64_t)s.w << 32) | s.z;
+        return st;
+    }
+    ZC_D static State shfl_state(const State& s, int src) {
+        State r;
+        r.cur = __shfl_sync(FULL_MASK, s.cur, src);
+        r.opp = __shfl_sync(FULL_MASK, s.opp, src);
+        return r;
+    }
+    ZC_HD static int move_slots(int) { return 0; }                    // moves are implied by the legal mask
+    ZC_HD static void store_moves(uint4*, const State&, uint32_t, int) {}
+    // state after the ei-th move (backend order) of `parent`
+    ZC_HD static State child(const State& parent, uint32_t, const uint4*, int, int ei, uint32_t& cmisc) {
+        cmisc = 0;
+        return c4::play(parent, c4::move_col(c4::legal_mask(parent), ei));
+    }
+    ZC_HD static int count_moves(const State& s, uint32_t) { return c4::n_moves(s); }
+    ZC_HD static double eval(const State& s, uint32_t, int evaluator) {
+        return evaluator == ZC_EVAL_C4_POSITIONAL ? c4::eval_positional(s) : c4::eval_terminal(s);
+    }
+    ZC_HD static double eval_child(const State& s, uint32_t m, int, int evaluator) { return eval(s, m, evaluator); }
+
+    // leaf -> network input row: plane 0 = side to move, plane 1 = opponent, [r][c] with r = 0 the top row
+    ZC_D static void pack_planes(void* planes, int dtype, size_t row, bool valid, bool in_range, const State& s, uint32_t) {
+        if (!in_range) return;
+        const uint32_t one16 = dtype == 2 ? 0x3C00u : 0x3F80u;   // f16 : bf16
+#pragma unroll 1
+        for (int q = 0; q < 21; ++q) {
+            uint32_t bits = 0;
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                const int idx = q * 4 + t, pl = idx / 42, cell = idx % 42, r = cell / 7, c = cell % 7;
+                const uint64_t bb = pl == 0 ? s.cur : s.opp;
+                bits |= (uint32_t)((bb >> (c * 7 + (5 - r))) & 1ull) << t;
+            }
+            if (!valid) bits = 0;
+            if (dtype == 1) {
+                float4 f = make_float4(bits & 1 ? 1.f : 0.f, bits & 2 ? 1.f : 0.f, bits & 4 ? 1.f : 0.f, bits & 8 ? 1.f : 0.f);
+                reinterpret_cast<float4*>(planes)[row * 21 + q] = f;
+            } else {
+                uint2 h;
+                h.x = (bits & 1 ? one16 : 0u) | (bits & 2 ? one16 << 16 : 0u);
+                h.y = (bits & 4 ? one16 : 0u) | (bits & 8 ? one16 << 16 : 0u);
+                reinterpret_cast<uint2*>(planes)[row * 21 + q] = h;
+            }
+        }
+    }
+};
+
+}  // namespace zc

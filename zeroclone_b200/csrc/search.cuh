@@ -1,0 +1,414 @@
+// Batched MCTS: one warp owns one tree.
+//
+// What is reproduced (engine/mcts/src/mcts.cpp, digest in SURVEY.md App. A): UCB1 selection
+// with statistics FROZEN for a batch of `batch_size` simulations (mcts.cpp:129-149), one new
+// node per simulation, evaluation of the batch, then backprop in pending order (:112-127).
+//
+// How it is restructured for the GPU.  With frozen statistics the `batch_size` descents of a
+// batch are not independent walks: every simulation of the batch re-walks the same argmax path
+// until it meets the first node that still has untried moves, and a freshly created child has
+// Na = 0 => UCT = +inf (mcts.cpp:43) => it wins the argmax at its parent.  So one batch is
+//     ONE frozen descent  root -> P                                   (warp-wide argmax per level)
+//   + a CHAIN: expand the untried moves of P (one lane per child), then step into P's
+//     lowest-index fresh child and expand ITS moves, ... until batch_size leaves exist;
+//     a move-less node ends the chain: it is evaluated again by every remaining simulation
+//   + one backprop pass: lane l owns path level l and applies the leaves' values to its edge
+//     strictly in pending order (same fp64 operation sequence as mcts.cpp:80-100).
+// This is exact, not an approximation: tests compare whole-tree hashes with the oracle.
+#pragma once
+#include <cuda_runtime.h>
+#include <math_constants.h>
+
+#include "tree.cuh"
+
+namespace zc {
+
+constexpr unsigned FULL_MASK = 0xFFFFFFFFu;
+
+struct SearchParams {
+    uint4* arena;            // [n_trees][arena_slots]
+    TreeCtl* ctl;            // [n_trees]
+    uint2* path;             // [n_trees][path_cap]  {node slot, edge index} per level
+    Pending* pending;        // [n_trees]  (split-phase only)
+    const double* log_tab;   // log_tab[n] = glibc log((double)n), filled on the host (mcts.cpp:44)
+    unsigned int* work_counter;
+    uint64_t arena_slots;
+    uint32_t path_cap;
+    int n_trees;
+    int simulations;         // per tree, this call
+    int batch_size;          // 1..32
+    int evaluator;
+    int policy;
+    double c;
+    uint64_t seed;
+    // split-phase leaf packing
+    void* planes;
+    int plane_dtype;
+    const float* values;
+};
+
+ZC_D uint4 shfl4(const uint4& v, int src) {
+    uint4 r;
+    r.x = __shfl_sync(FULL_MASK, v.x, src);
+    r.y = __shfl_sync(FULL_MASK, v.y, src);
+    r.z = __shfl_sync(FULL_MASK, v.z, src);
+    r.w = __shfl_sync(FULL_MASK, v.w, src);
+    return r;
+}
+ZC_D int warp_excl_scan(int v, int lane, int& total) {
+    int x = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        int y = __shfl_up_sync(FULL_MASK, x, d);
+        if (lane >= d) x += y;
+    }
+    total = __shfl_sync(FULL_MASK, x, 31);
+    return x - v;
+}
+
+// j-th move to be expanded at a node with k moves (mcts.cpp:65-78 with policy = first / last
+// element of the untried list; both keep `untried` an interval, so the order is a function of j)
+ZC_D int expansion_order(int policy, int k, int j) { return policy == 1 /*ZC_POLICY_LAST*/ ? k - 1 - j : j; }
+
+// UCB1, mcts.cpp:41-45, with the operation sequence of the reference build
+// (log; divide; sqrt; FUSED multiply-add -- see oracle/zc_oracle.c:uct).
+ZC_D double uct(double W, int Na, double logN, double c) {
+    if (Na == 0) return CUDART_INF;
+    const double na = (double)Na;
+    const double q = __ddiv_rn(W, na);                       // Qa as stored at mcts.cpp:93
+    return __fma_rn(__dsqrt_rn(__ddiv_rn(logN, na)), c, q);
+}
+
+// ---------------------------------------------------------------------------------------------
+// select + expand one batch for one tree.  Leaves end up one per lane (lane i = pending[i]).
+// Returns false if the arena overflowed (tree is then flagged and abandoned).
+// ---------------------------------------------------------------------------------------------
+template <class G>
+struct Leaf {
+    uint32_t info;          // LEAF_* encoding, 0 on lanes >= B
+    double value;           // built-in evaluators only
+    typename G::State st;   // leaf state (for plane packing)
+    uint32_t misc;
+};
+
+template <class G, bool kBuiltinEval>
+ZC_D bool select_expand(const SearchParams& p, uint4* __restrict__ arena, uint2* __restrict__ path, TreeCtl& ctl,
+                        int B, int lane, int& D_out, Leaf<G>& leaf) {
+    // ---- frozen descent (mcts.cpp:47-63)
+    uint32_t node = 0;
+    int depth = 0;
+    uint4 hdr;
+    typename G::State st;
+    uint32_t misc;
+    for (;;) {
+        const uint4* np = arena + node;
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (lane < G::FIRST_SLOTS) v = np[lane];
+        hdr = shfl4(v, 0);
+        misc = hdr_misc(hdr);
+        st = G::state_from_lanes(v);
+        const int k = (int)hdr_k(hdr), nexp = (int)hdr_nexp(hdr);
+        if (nexp < k || k == 0) break;
+        const double logN = p.log_tab[hdr.x];
+        double best = -CUDART_INF;
+        int best_e = 0x7FFFFFFF;
+        uint32_t best_child = 0;
+        {
+            const int e = lane - (1 + G::SS);
+            if (e >= 0 && e < k && lane < G::FIRST_SLOTS) {
+                best = uct(edge_W(v), (int)v.z, logN, p.c);
+                best_e = e;
+                best_child = v.w;
+            }
+        }
+        for (int e = G::FIRST_SLOTS - (1 + G::SS) + lane; e < k; e += 32) {   // wide nodes (chess)
+            const uint4 ev = np[1 + G::SS + e];
+            const double u = uct(edge_W(ev), (int)ev.z, logN, p.c);
+            if (u > best) { best = u; best_e = e; best_child = ev.w; }       // ascending e: strict > keeps the lowest
+        }
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) {
+            const double ob = __shfl_xor_sync(FULL_MASK, best, d);
+            const int oe = __shfl_xor_sync(FULL_MASK, best_e, d);
+            const uint32_t oc = __shfl_xor_sync(FULL_MASK, best_child, d);
+            if (ob > best || (ob == best && oe < best_e)) { best = ob; best_e = oe; best_child = oc; }
+        }
+        if (lane == 0) path[depth] = make_uint2(node, (uint32_t)best_e);
+        ctl.sum_path_children += (unsigned)k;
+        node = best_child;
+        ++depth;
+        if ((uint32_t)depth + 34u >= p.path_cap) { ctl.status = -4; return false; }
+    }
+
+    // ---- chain of expansions (mcts.cpp:65-78 applied batch_size times to frozen statistics)
+    uint32_t P = node;
+    int Pk = (int)hdr_k(hdr), Pnexp = (int)hdr_nexp(hdr);
+    typename G::State Pst = st;
+    uint32_t Pmisc = misc;
+    int D = depth, made = 0;
+    leaf.info = 0;
+    leaf.value = 0.0;
+    leaf.st = st;
+    leaf.misc = misc;
+    while (made < B) {
+        if (Pk == 0) {                       // move-less node: select() returns it again and again (:59)
+            if (lane >= made && lane < B) {
+                leaf.info = LEAF_SELF | (uint32_t)D;
+                leaf.st = Pst;
+                leaf.misc = Pmisc;
+                if (kBuiltinEval) leaf.value = G::eval(Pst, Pmisc, p.evaluator);
+            }
+            ctl.reevaluated += (uint32_t)(B - made);
+            ctl.sum_leaf_depth += (unsigned long long)(B - made) * (unsigned)D;
+            ctl.max_leaf_depth = max(ctl.max_leaf_depth, (uint32_t)D);
+            made = B;
+            break;
+        }
+        const int m = min(Pk - Pnexp, B - made);
+        const int j = lane - made;
+        const bool act = j >= 0 && j < m;
+        int ei = 0x7FFFFFFF, ck = 0;
+        typename G::State cs = Pst;
+        uint32_t cmisc = 0;
+        if (act) {
+            ei = expansion_order(p.policy, Pk, Pnexp + j);
+            cs = G::child(Pst, Pmisc, arena + P, Pk, ei, cmisc);
+            ck = G::count_moves(cs, cmisc);
+        }
+        const int csize = act ? 1 + G::SS + ck + G::move_slots(ck) : 0;
+        int total;
+        const int off = warp_excl_scan(csize, lane, total);
+        if ((uint64_t)ctl.top + (uint64_t)total > p.arena_slots) { ctl.status = -4; return false; }
+        const uint32_t base = ctl.top;
+        for (int t = lane; t < total; t += 32) arena[base + t] = make_uint4(0, 0, 0, 0);   // edges start at Na=0, Wa=0, no child
+        __syncwarp();
+        uint32_t my_slot = 0;
+        if (act) {
+            my_slot = base + (uint32_t)off;
+            arena[my_slot] = make_hdr(0, (uint32_t)ck, 0, P, (uint32_t)ei, cmisc, (uint32_t)(D + 1));
+            G::store_state(arena + my_slot + 1, cs);
+            G::store_moves(arena + my_slot + 1 + G::SS + ck, cs, cmisc, ck);
+            arena[P + 1 + G::SS + ei].w = my_slot;                     // children[move_idx] = child (:76)
+            leaf.info = (uint32_t)D | ((uint32_t)ei << LEAF_EDGE_SHIFT);
+            leaf.st = cs;
+            leaf.misc = cmisc;
+            if (kBuiltinEval) leaf.value = G::eval_child(cs, cmisc, ck, p.evaluator);
+        }
+        Pnexp += m;
+        if (lane == 0) arena[P].y = (uint32_t)Pk | ((uint32_t)Pnexp << 16);   // untried.erase (:72)
+        ctl.top += (uint32_t)total;
+        ctl.nodes += (uint32_t)m;
+        ctl.sum_leaf_depth += (unsigned long long)m * (unsigned)(D + 1);
+        ctl.max_leaf_depth = max(ctl.max_leaf_depth, (uint32_t)(D + 1));
+        made += m;
+        if (made >= B) break;
+        // P is fully expanded and simulations remain: UCT = +inf for every fresh child, the
+        // lowest move index among them wins (mcts.cpp:43,57).
+        int min_e = ei;
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) min_e = min(min_e, __shfl_xor_sync(FULL_MASK, min_e, d));
+        const unsigned who = __ballot_sync(FULL_MASK, act && ei == min_e);
+        const int src = __ffs((int)who) - 1;
+        if (lane == src) leaf.info |= LEAF_PATH;
+        if (lane == 0) path[D] = make_uint2(P, (uint32_t)min_e);
+        ctl.sum_path_children += (unsigned)Pk;
+        P = __shfl_sync(FULL_MASK, my_slot, src);
+        Pst = G::shfl_state(cs, src);
+        Pmisc = __shfl_sync(FULL_MASK, cmisc, src);
+        Pk = __shfl_sync(FULL_MASK, ck, src);
+        Pnexp = 0;
+        ++D;
+        if ((uint32_t)D + 2u >= p.path_cap) { ctl.status = -4; return false; }
+    }
+    if (lane == 0) path[D] = make_uint2(P, 0xFFFFFFFFu);
+    __syncwarp();
+    D_out = D;
+    return true;
+}
+
+// ---------------------------------------------------------------------------------------------
+// backprop of one batch in pending order (mcts.cpp:80-100, 120-124).
+// lane i holds leaf i (info, value); lane l then owns path level l.
+// ---------------------------------------------------------------------------------------------
+template <class G>
+ZC_D void backprop_batch(uint4* __restrict__ arena, const uint2* __restrict__ path, int B, int D, int lane,
+                         uint32_t info, double value) {
+    // leaves that are not on the chain: their node and their edge see exactly one backprop
+    if (lane < B && !(info & (LEAF_SELF | LEAF_PATH))) {
+        const int li = (int)(info & LEAF_LEVEL_MASK);
+        const int e = (int)((info >> LEAF_EDGE_SHIFT) & 0xFFu);
+        const uint32_t parent = path[li].x;
+        uint4* ep = arena + parent + 1 + G::SS + e;
+        const uint32_t child = ep->w;
+        uint4 nv;
+        edge_set_W(nv, 0.0 - value);      // Wa -= result, from Wa = 0
+        nv.z = 1;
+        nv.w = child;
+        *ep = nv;
+        arena[child].x = 1;               // node->N += 1
+    }
+    for (int base = 0; base <= D; base += 32) {
+        const int l = base + lane;
+        const bool on = l <= D;
+        uint32_t node = 0, a = 0, N = 0;
+        uint4 edge = make_uint4(0, 0, 0, 0);
+        uint4* ep = nullptr;
+        if (on) {
+            const uint2 pe = path[l];
+            node = pe.x;
+            a = pe.y;
+            N = arena[node].x;
+            if (l < D) {
+                ep = arena + node + 1 + G::SS + a;
+                edge = *ep;
+            }
+        }
+        double W = edge_W(edge);
+        int Na = (int)edge.z;
+        for (int i = 0; i < B; ++i) {
+            const uint32_t inf = __shfl_sync(FULL_MASK, info, i);
+            const double v = __shfl_sync(FULL_MASK, value, i);
+            const int li = (int)(inf & LEAF_LEVEL_MASK);
+            const bool self = (inf & LEAF_SELF) != 0, onpath = (inf & LEAF_PATH) != 0;
+            const int leaf_depth = self ? li : li + 1;
+            if (li >= l || (onpath && li + 1 == l)) ++N;                      // node->N += 1 along the parent chain
+            if (l < D && (li > l || (li == l && onpath))) {
+                ++Na;                                                         // parent->Na[a] += 1
+                W = W - (((leaf_depth - l - 1) & 1) ? -v : v);                // parent->Wa[a] -= result; result = -result
+            }
+        }
+        if (on) {
+            arena[node].x = N;
+            if (l < D) {
+                edge_set_W(edge, W);
+                edge.z = (uint32_t)Na;
+                *ep = edge;
+            }
+        }
+    }
+    __syncwarp();
+}
+
+// ---------------------------------------------------------------------------------------------
+// kernels
+// ---------------------------------------------------------------------------------------------
+constexpr int SEARCH_BLOCK = 128;
+
+// Fused persistent search with a built-in evaluator: the whole simulation loop of get_move
+// (mcts.cpp:129-149) for every tree.  Warps pull tree indices from a global counter.
+template <class G>
+__global__ void __launch_bounds__(SEARCH_BLOCK) k_search_fused(SearchParams p) {
+    const int lane = threadIdx.x & 31;
+    for (;;) {
+        int tree = 0;
+        if (lane == 0) tree = (int)atomicAdd(p.work_counter, 1u);
+        tree = __shfl_sync(FULL_MASK, tree, 0);
+        if (tree >= p.n_trees) return;
+        uint4* arena = p.arena + (uint64_t)tree * p.arena_slots;
+        uint2* path = p.path + (uint64_t)tree * p.path_cap;
+        TreeCtl ctl = p.ctl[tree];
+        for (int done = 0; done < p.simulations && ctl.status == 0;) {
+            const int B = min(p.batch_size, p.simulations - done);
+            int D;
+            Leaf<G> leaf;
+            if (!select_expand<G, true>(p, arena, path, ctl, B, lane, D, leaf)) break;
+            backprop_batch<G>(arena, path, B, D, lane, leaf.info, leaf.value);
+            done += B;
+            ctl.sims_done += (uint32_t)B;
+        }
+        if (lane == 0) p.ctl[tree] = ctl;
+    }
+}
+
+// Split phase 1 (external evaluator): select+expand one batch per tree, pack leaf planes.
+template <class G>
+__global__ void __launch_bounds__(SEARCH_BLOCK) k_select(SearchParams p, int sims_left) {
+    const int lane = threadIdx.x & 31;
+    const int tree = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
+    if (tree >= p.n_trees) return;
+    uint4* arena = p.arena + (uint64_t)tree * p.arena_slots;
+    uint2* path = p.path + (uint64_t)tree * p.path_cap;
+    TreeCtl ctl = p.ctl[tree];
+    Pending* pd = p.pending + tree;
+    const int B = ctl.status == 0 ? min(p.batch_size, sims_left) : 0;
+    int D = 0;
+    Leaf<G> leaf;
+    leaf.info = 0;
+    bool ok = B > 0;
+    if (ok) ok = select_expand<G, false>(p, arena, path, ctl, B, lane, D, leaf);
+    if (lane == 0) {
+        pd->B = ok ? B : 0;
+        pd->D = D;
+        p.ctl[tree] = ctl;
+    }
+    pd->info[lane] = ok ? leaf.info : 0u;
+    G::pack_planes(p.planes, p.plane_dtype, (size_t)tree * (size_t)p.batch_size + (size_t)lane,
+                   ok && lane < B, lane < p.batch_size, leaf.st, leaf.misc);
+}
+
+// Split phase 2: backprop the batch with the caller's values.
+template <class G>
+__global__ void __launch_bounds__(SEARCH_BLOCK) k_backprop(SearchParams p) {
+    const int lane = threadIdx.x & 31;
+    const int tree = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
+    if (tree >= p.n_trees) return;
+    Pending* pd = p.pending + tree;
+    const int B = pd->B;
+    if (B == 0) return;
+    uint4* arena = p.arena + (uint64_t)tree * p.arena_slots;
+    const uint2* path = p.path + (uint64_t)tree * p.path_cap;
+    const uint32_t info = pd->info[lane];
+    double v = 0.0;
+    if (lane < B) v = (double)p.values[(size_t)tree * (size_t)p.batch_size + (size_t)lane];
+    backprop_batch<G>(arena, path, B, pd->D, lane, info, v);
+    if (lane == 0) {
+        p.ctl[tree].sims_done += (uint32_t)B;
+        pd->B = 0;
+    }
+}
+
+// Whole-tree hash, one thread per tree, stackless depth-first walk (children in move order).
+// Must equal oracle/zc_oracle.c:hash_tree.
+template <class G>
+__global__ void k_tree_hash(const uint4* __restrict__ arena_all, uint64_t arena_slots, int n_trees,
+                            unsigned long long* __restrict__ out) {
+    const int tree = blockIdx.x * blockDim.x + threadIdx.x;
+    if (tree >= n_trees) return;
+    const uint4* arena = arena_all + (uint64_t)tree * arena_slots;
+    unsigned long long h = 0x5A17C10E5EEDull;
+    uint32_t node = 0;
+    uint32_t i = 0;
+    bool entering = true;
+    for (;;) {
+        const uint4 hd = arena[node];
+        const uint32_t k = hdr_k(hd);
+        if (entering) {
+            h = mix64(h, ((unsigned long long)hdr_depth(hd) << 48) ^ ((unsigned long long)k << 32) ^
+                             ((unsigned long long)(k - hdr_nexp(hd)) << 20) ^ (unsigned long long)hd.x);
+            i = 0;
+            entering = false;
+        }
+        bool descended = false;
+        while (i < k) {
+            const uint4 e = arena[node + 1 + G::SS + i];
+            double w = edge_W(e);
+            if (w == 0.0) w = 0.0;   // fold -0.0
+            h = mix64(h, ((unsigned long long)i << 40) ^ ((unsigned long long)e.z << 1) ^ (e.w ? 1ull : 0ull));
+            h = mix64(h, (unsigned long long)__double_as_longlong(w));
+            if (e.w) {
+                node = e.w;
+                entering = true;
+                descended = true;
+                break;
+            }
+            ++i;
+        }
+        if (descended) continue;
+        if (node == 0) break;
+        i = hdr_parent_edge(hd) + 1;
+        node = hd.z;
+    }
+    out[tree] = h;
+}
+
+}  // namespace zc

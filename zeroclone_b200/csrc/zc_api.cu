@@ -1,0 +1,469 @@
+// libzc_b200.so -- C-ABI (include/zc_b200.h) over the CUDA search kernels.
+// Host side: handle bookkeeping, launches, copies.  No CPU implementation of the search exists.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/zc_b200.h"
+#include "c4_game.cuh"
+#include "search.cuh"
+
+namespace zc {
+namespace c4 {
+// CPython 3.12 set order; replaced at import by the Python host
+uint32_t h_order[128];
+static const uint8_t kDefaultOrder[128][8] = {
+#include "c4_order_py312.inc"
+};
+}  // namespace c4
+}  // namespace zc
+
+using namespace zc;
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+#define CUDA_TRY(expr)                                                                         \
+    do {                                                                                       \
+        cudaError_t _e = (expr);                                                               \
+        if (_e != cudaSuccess)                                                                 \
+            return fail(ZC_ECUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));         \
+    } while (0)
+
+struct zc_search {
+    int game = 0, device = 0, max_trees = 0, max_sims = 0, n_trees = 0;
+    uint64_t arena_slots = 0;
+    uint32_t path_cap = 0;
+    uint4* arena = nullptr;
+    TreeCtl* ctl = nullptr;
+    uint2* path = nullptr;
+    Pending* pending = nullptr;
+    double* log_tab = nullptr;
+    unsigned int* work_counter = nullptr;
+    void* roots_dev = nullptr;          // staging for host roots
+    zc_root_result* res_dev = nullptr;
+    int32_t* visits_dev = nullptr;
+    double* wsum_dev = nullptr;
+    zc_chess_move* moves_dev = nullptr;
+    int res_stride = 0;
+    unsigned long long* hash_dev = nullptr;
+    int64_t bytes = 0;
+    int64_t launches = 0;
+    int fused_grid = 0;
+    int order_version = 0;
+    // split-phase state
+    int sp_left = 0, sp_batch = 0, sp_policy = 0, sp_selected = 0;
+    double sp_c = 1.4;
+    uint64_t sp_seed = 0;
+};
+
+// ------------------------------------------------------------------------------- C4 move order
+static bool g_order_ready = false;
+static int g_order_version = 1;
+static void pack_order(const uint8_t* table) {
+    for (int m = 0; m < 128; ++m) {
+        uint32_t w = 0;
+        for (int i = 0; i < 7 && table[m * 8 + i] != 255; ++i) w |= (uint32_t)(table[m * 8 + i] & 0xF) << (4 * i);
+        c4::h_order[m] = w;
+    }
+    g_order_ready = true;
+}
+static void ensure_order() {
+    if (!g_order_ready) pack_order(&c4::kDefaultOrder[0][0]);
+}
+static int upload_order() {
+    ensure_order();
+    CUDA_TRY(cudaMemcpyToSymbol(c4::d_order, c4::h_order, sizeof(c4::h_order)));
+    return ZC_OK;
+}
+
+extern "C" int zc_c4_set_move_order(const uint8_t* table) {
+    if (!table) return fail(ZC_EINVAL, "table is NULL");
+    for (int m = 0; m < 128; ++m) {   // every row must be a permutation of the mask's columns
+        int seen = 0, n = 0;
+        for (; n < 7 && table[m * 8 + n] != 255; ++n) {
+            if (table[m * 8 + n] > 6) return fail(ZC_EINVAL, "move order: column out of range");
+            seen |= 1 << table[m * 8 + n];
+        }
+        if (seen != m || n != __builtin_popcount(m)) return fail(ZC_EINVAL, "move order: row is not a permutation of its mask");
+    }
+    pack_order(table);
+    ++g_order_version;   // handles re-upload to their device at the next set_roots
+    return ZC_OK;
+}
+extern "C" int zc_c4_get_move_order(uint8_t* table) {
+    if (!table) return fail(ZC_EINVAL, "table is NULL");
+    ensure_order();
+    memset(table, 255, 128 * 8);
+    for (int m = 0; m < 128; ++m)
+        for (int i = 0; i < __builtin_popcount(m); ++i) table[m * 8 + i] = (uint8_t)((c4::h_order[m] >> (4 * i)) & 0xF);
+    return ZC_OK;
+}
+
+extern "C" int zc_abi_version(void) { return ZC_ABI_VERSION; }
+extern "C" const char* zc_last_error(void) { return g_err.c_str(); }
+extern "C" int zc_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+// ------------------------------------------------------------------------------- kernels local to the API
+__global__ void k_set_roots_c4(const zc_c4_state* __restrict__ roots, uint4* __restrict__ arena_all, uint64_t arena_slots,
+                               TreeCtl* __restrict__ ctl, Pending* __restrict__ pending, int n) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const zc_c4_state r = roots[t];
+    c4::State s;
+    s.cur = r.turn == 0 ? r.x : r.o;
+    s.opp = r.turn == 0 ? r.o : r.x;
+    const int k = c4::n_moves(s);
+    uint4* arena = arena_all + (uint64_t)t * arena_slots;
+    arena[0] = make_hdr(0, (uint32_t)k, 0, 0, 0, 0, 0);
+    C4Game::store_state(arena + 1, s);
+    for (int i = 0; i < k; ++i) arena[2 + i] = make_uint4(0, 0, 0, 0);
+    TreeCtl c;
+    memset(&c, 0, sizeof c);
+    c.top = (uint32_t)(2 + k);
+    c.nodes = 1;
+    c.root_turn = (uint32_t)r.turn;
+    ctl[t] = c;
+    pending[t].B = 0;
+}
+
+__global__ void k_results_c4(const uint4* __restrict__ arena_all, uint64_t arena_slots, const TreeCtl* __restrict__ ctl,
+                             int n, zc_root_result* __restrict__ res, int32_t* __restrict__ visits,
+                             double* __restrict__ wsum, zc_chess_move* __restrict__ moves, int stride) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const uint4* arena = arena_all + (uint64_t)t * arena_slots;
+    const uint4 hd = arena[0];
+    const int k = (int)hdr_k(hd);
+    const c4::State s = C4Game::load_state(arena + 1);
+    const int mask = c4::legal_mask(s);
+    int best = -1, best_n = -1;
+    for (int i = 0; i < k; ++i) {
+        const uint4 e = arena[2 + i];
+        if (e.w && (int)e.z > best_n) { best_n = (int)e.z; best = i; }      // mcts.cpp:150-155
+        if (i < stride) {
+            if (visits) visits[(size_t)t * stride + i] = (int)e.z;
+            if (wsum) wsum[(size_t)t * stride + i] = edge_W(e);
+            if (moves) {
+                zc_chess_move mv;
+                mv.fr = (uint8_t)c4::move_col(mask, i);
+                mv.fc = mv.tr = mv.tc = 0;
+                mv.value = 0.f;
+                moves[(size_t)t * stride + i] = mv;
+            }
+        }
+    }
+    const TreeCtl c = ctl[t];
+    zc_root_result r;
+    memset(&r, 0, sizeof r);
+    r.n_moves = k;
+    r.best = best;
+    r.root_visits = (int)hd.x;
+    r.status = c.status;
+    r.best_move[0] = best >= 0 ? (uint8_t)c4::move_col(mask, best) : 255;
+    r.nodes = (int)c.nodes;
+    r.sum_leaf_depth = (int64_t)c.sum_leaf_depth;
+    r.max_leaf_depth = (int)c.max_leaf_depth;
+    r.reevaluated_leaves = (int)c.reevaluated;
+    res[t] = r;
+}
+
+// ------------------------------------------------------------------------------- handle
+static int check_handle(const zc_search* h) {
+    if (!h) return fail(ZC_EINVAL, "handle is NULL");
+    return ZC_OK;
+}
+
+extern "C" int zc_search_create(int game, int device, int max_trees, int max_sims, int64_t arena_slots_per_tree,
+                                zc_search** out) {
+    if (!out) return fail(ZC_EINVAL, "out is NULL");
+    *out = nullptr;
+    if (game != ZC_GAME_C4) return fail(ZC_EINVAL, "unknown game");
+    if (max_trees < 1 || max_sims < 1) return fail(ZC_EINVAL, "max_trees and max_sims must be >= 1");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(ZC_ENODEVICE, "no CUDA device: libzc_b200 has no CPU path");
+    }
+    if (device < 0 || device >= ndev) return fail(ZC_EINVAL, "device out of range");
+    CUDA_TRY(cudaSetDevice(device));
+    zc_search* h = new zc_search();
+    h->game = game;
+    h->device = device;
+    h->max_trees = max_trees;
+    h->max_sims = max_sims;
+    const int per_node = game == ZC_GAME_C4 ? 1 + C4Game::SS + 7 : 48;
+    h->arena_slots = arena_slots_per_tree > 0 ? (uint64_t)arena_slots_per_tree : (uint64_t)(max_sims + 1) * per_node;
+    h->arena_slots = (h->arena_slots + 1) & ~1ull;   // keep every tree's arena 32-byte aligned
+    h->path_cap = (uint32_t)max_sims + 40u;
+    auto alloc = [&](void** p, size_t bytes) -> cudaError_t {
+        h->bytes += (int64_t)bytes;
+        return cudaMalloc(p, bytes);
+    };
+    const size_t arena_bytes = ((size_t)max_trees * h->arena_slots + 64) * sizeof(uint4);   // +64: speculative node loads
+    cudaError_t e = cudaSuccess;
+    if (e == cudaSuccess) e = alloc((void**)&h->arena, arena_bytes);
+    if (e == cudaSuccess) e = alloc((void**)&h->ctl, sizeof(TreeCtl) * max_trees);
+    if (e == cudaSuccess) e = alloc((void**)&h->path, sizeof(uint2) * (size_t)max_trees * h->path_cap);
+    if (e == cudaSuccess) e = alloc((void**)&h->pending, sizeof(Pending) * max_trees);
+    if (e == cudaSuccess) e = alloc((void**)&h->log_tab, sizeof(double) * ((size_t)max_sims + 4));
+    if (e == cudaSuccess) e = alloc((void**)&h->work_counter, sizeof(unsigned int));
+    if (e == cudaSuccess) e = alloc((void**)&h->roots_dev, sizeof(zc_chess_state) * max_trees);
+    if (e == cudaSuccess) e = alloc((void**)&h->res_dev, sizeof(zc_root_result) * max_trees);
+    if (e == cudaSuccess) e = alloc((void**)&h->hash_dev, sizeof(unsigned long long) * max_trees);
+    if (e != cudaSuccess) {
+        std::string msg = std::string("cudaMalloc: ") + cudaGetErrorString(e);
+        zc_search_destroy(h);
+        return fail(ZC_ECUDA, msg);
+    }
+    // log table from the HOST libm: the reference calls glibc's log (mcts.cpp:44), which is not
+    // correctly rounded, so the device must use the very same values to stay bit-exact.
+    std::vector<double> lt((size_t)max_sims + 4);
+    lt[0] = -INFINITY;
+    for (size_t i = 1; i < lt.size(); ++i) {
+        volatile double x = (double)i;
+        lt[i] = std::log(x);
+    }
+    CUDA_TRY(cudaMemcpy(h->log_tab, lt.data(), lt.size() * sizeof(double), cudaMemcpyHostToDevice));
+    int occ = 0, sms = 0;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_search_fused<C4Game>, SEARCH_BLOCK, 0));
+    CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    h->fused_grid = occ * sms;
+    *out = h;
+    return ZC_OK;
+}
+
+extern "C" int zc_search_destroy(zc_search* h) {
+    if (!h) return ZC_OK;
+    cudaSetDevice(h->device);
+    cudaFree(h->arena);
+    cudaFree(h->ctl);
+    cudaFree(h->path);
+    cudaFree(h->pending);
+    cudaFree(h->log_tab);
+    cudaFree(h->work_counter);
+    cudaFree(h->roots_dev);
+    cudaFree(h->res_dev);
+    cudaFree(h->visits_dev);
+    cudaFree(h->wsum_dev);
+    cudaFree(h->moves_dev);
+    cudaFree(h->hash_dev);
+    delete h;
+    return ZC_OK;
+}
+
+extern "C" int64_t zc_search_device_bytes(const zc_search* h) { return h ? h->bytes : 0; }
+
+static int set_roots_common(zc_search* h, const void* dev_states, int n, cudaStream_t st) {
+    h->n_trees = n;
+    h->sp_left = 0;
+    if (h->order_version != g_order_version) {
+        if (int rc = upload_order()) return rc;
+        h->order_version = g_order_version;
+    }
+    k_set_roots_c4<<<(n + 127) / 128, 128, 0, st>>>((const zc_c4_state*)dev_states, h->arena, h->arena_slots, h->ctl,
+                                                  h->pending, n);
+    h->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return ZC_OK;
+}
+
+extern "C" int zc_search_set_roots(zc_search* h, const void* host_states, int n, void* stream) {
+    if (int rc = check_handle(h)) return rc;
+    if (!host_states || n < 1 || n > h->max_trees) return fail(ZC_EINVAL, "set_roots: bad states or n");
+    CUDA_TRY(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t sz = h->game == ZC_GAME_C4 ? sizeof(zc_c4_state) : sizeof(zc_chess_state);
+    CUDA_TRY(cudaMemcpyAsync(h->roots_dev, host_states, sz * n, cudaMemcpyHostToDevice, st));
+    if (int rc = set_roots_common(h, h->roots_dev, n, st)) return rc;
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return ZC_OK;
+}
+
+extern "C" int zc_search_set_roots_dev(zc_search* h, const void* dev_states, int n, void* stream) {
+    if (int rc = check_handle(h)) return rc;
+    if (!dev_states || n < 1 || n > h->max_trees) return fail(ZC_EINVAL, "set_roots_dev: bad states or n");
+    CUDA_TRY(cudaSetDevice(h->device));
+    return set_roots_common(h, dev_states, n, (cudaStream_t)stream);
+}
+
+static SearchParams make_params(zc_search* h, int sims, double c, int batch, int evaluator, int policy, uint64_t seed) {
+    SearchParams p;
+    memset(&p, 0, sizeof p);
+    p.arena = h->arena;
+    p.ctl = h->ctl;
+    p.path = h->path;
+    p.pending = h->pending;
+    p.log_tab = h->log_tab;
+    p.work_counter = h->work_counter;
+    p.arena_slots = h->arena_slots;
+    p.path_cap = h->path_cap;
+    p.n_trees = h->n_trees;
+    p.simulations = sims;
+    p.batch_size = batch;
+    p.evaluator = evaluator;
+    p.policy = policy;
+    p.c = c;
+    p.seed = seed;
+    return p;
+}
+
+static int check_search_args(zc_search* h, int sims, int batch, int policy) {
+    if (h->n_trees < 1) return fail(ZC_ESTATE, "no roots set");
+    if (sims < 0 || sims > h->max_sims) return fail(ZC_EINVAL, "simulations exceeds max_sims of the handle");
+    if (batch < 1 || batch > 32) return fail(ZC_EINVAL, "batch_size must be in 1..32");
+    if (policy != ZC_POLICY_FIRST && policy != ZC_POLICY_LAST) return fail(ZC_EINVAL, "unsupported policy");
+    return ZC_OK;
+}
+
+extern "C" int zc_search_run(zc_search* h, int simulations, double c, int batch_size, int evaluator, int policy,
+                             uint64_t seed, void* stream) {
+    if (int rc = check_handle(h)) return rc;
+    if (int rc = check_search_args(h, simulations, batch_size, policy)) return rc;
+    if (evaluator != ZC_EVAL_C4_TERMINAL && evaluator != ZC_EVAL_C4_POSITIONAL)
+        return fail(ZC_EINVAL, "evaluator is not a built-in evaluator of this game");
+    CUDA_TRY(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    SearchParams p = make_params(h, simulations, c, batch_size, evaluator, policy, seed);
+    CUDA_TRY(cudaMemsetAsync(h->work_counter, 0, sizeof(unsigned int), st));
+    const int blocks_needed = (h->n_trees * 32 + SEARCH_BLOCK - 1) / SEARCH_BLOCK;
+    const int grid = blocks_needed < h->fused_grid ? blocks_needed : h->fused_grid;
+    k_search_fused<C4Game><<<grid, SEARCH_BLOCK, 0, st>>>(p);
+    h->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return ZC_OK;
+}
+
+extern "C" int zc_search_begin(zc_search* h, int simulations, double c, int batch_size, int policy, uint64_t seed) {
+    if (int rc = check_handle(h)) return rc;
+    if (int rc = check_search_args(h, simulations, batch_size, policy)) return rc;
+    h->sp_left = simulations;
+    h->sp_batch = batch_size;
+    h->sp_policy = policy;
+    h->sp_c = c;
+    h->sp_seed = seed;
+    h->sp_selected = 0;
+    return ZC_OK;
+}
+extern "C" int zc_search_pending(const zc_search* h) { return h ? h->sp_left : 0; }
+
+extern "C" int zc_search_select(zc_search* h, void* dev_planes, int plane_dtype, void* stream) {
+    if (int rc = check_handle(h)) return rc;
+    if (h->sp_left <= 0) return fail(ZC_ESTATE, "select: no simulations pending (call zc_search_begin)");
+    if (h->sp_selected) return fail(ZC_ESTATE, "select: previous batch not backpropagated");
+    if (!dev_planes || plane_dtype < 0 || plane_dtype > 2) return fail(ZC_EINVAL, "select: bad planes or dtype");
+    CUDA_TRY(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    SearchParams p = make_params(h, h->sp_left, h->sp_c, h->sp_batch, ZC_EVAL_EXTERNAL, h->sp_policy, h->sp_seed);
+    p.planes = dev_planes;
+    p.plane_dtype = plane_dtype;
+    const int grid = (h->n_trees * 32 + SEARCH_BLOCK - 1) / SEARCH_BLOCK;
+    k_select<C4Game><<<grid, SEARCH_BLOCK, 0, st>>>(p, h->sp_left);
+    h->launches++;
+    CUDA_TRY(cudaGetLastError());
+    h->sp_selected = h->sp_left < h->sp_batch ? h->sp_left : h->sp_batch;
+    return ZC_OK;
+}
+
+extern "C" int zc_search_backprop(zc_search* h, const float* dev_values, void* stream) {
+    if (int rc = check_handle(h)) return rc;
+    if (!h->sp_selected) return fail(ZC_ESTATE, "backprop: nothing selected");
+    if (!dev_values) return fail(ZC_EINVAL, "backprop: values is NULL");
+    CUDA_TRY(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    SearchParams p = make_params(h, h->sp_left, h->sp_c, h->sp_batch, ZC_EVAL_EXTERNAL, h->sp_policy, h->sp_seed);
+    p.values = dev_values;
+    const int grid = (h->n_trees * 32 + SEARCH_BLOCK - 1) / SEARCH_BLOCK;
+    k_backprop<C4Game><<<grid, SEARCH_BLOCK, 0, st>>>(p);
+    h->launches++;
+    CUDA_TRY(cudaGetLastError());
+    h->sp_left -= h->sp_selected;
+    h->sp_selected = 0;
+    return ZC_OK;
+}
+
+extern "C" int zc_search_results(zc_search* h, zc_root_result* results, int32_t* visits, double* value_sums,
+                                 zc_chess_move* moves, int stride, void* stream) {
+    if (int rc = check_handle(h)) return rc;
+    if (!results) return fail(ZC_EINVAL, "results is NULL");
+    if (h->n_trees < 1) return fail(ZC_ESTATE, "no roots set");
+    if ((visits || value_sums || moves) && (stride < 1 || stride > ZC_MAX_MOVES)) return fail(ZC_EINVAL, "bad stride");
+    CUDA_TRY(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int n = h->n_trees;
+    if (stride > h->res_stride && (visits || value_sums || moves)) {
+        cudaFree(h->visits_dev);
+        cudaFree(h->wsum_dev);
+        cudaFree(h->moves_dev);
+        h->visits_dev = nullptr; h->wsum_dev = nullptr; h->moves_dev = nullptr;
+        CUDA_TRY(cudaMalloc((void**)&h->visits_dev, sizeof(int32_t) * (size_t)h->max_trees * stride));
+        CUDA_TRY(cudaMalloc((void**)&h->wsum_dev, sizeof(double) * (size_t)h->max_trees * stride));
+        CUDA_TRY(cudaMalloc((void**)&h->moves_dev, sizeof(zc_chess_move) * (size_t)h->max_trees * stride));
+        h->res_stride = stride;
+    }
+    if (visits || value_sums || moves) {
+        CUDA_TRY(cudaMemsetAsync(h->visits_dev, 0, sizeof(int32_t) * (size_t)n * stride, st));
+        CUDA_TRY(cudaMemsetAsync(h->wsum_dev, 0, sizeof(double) * (size_t)n * stride, st));
+        CUDA_TRY(cudaMemsetAsync(h->moves_dev, 0, sizeof(zc_chess_move) * (size_t)n * stride, st));
+    }
+    k_results_c4<<<(n + 127) / 128, 128, 0, st>>>(h->arena, h->arena_slots, h->ctl, n, h->res_dev,
+                                                visits ? h->visits_dev : nullptr, value_sums ? h->wsum_dev : nullptr,
+                                                moves ? h->moves_dev : nullptr, stride);
+    h->launches++;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(results, h->res_dev, sizeof(zc_root_result) * n, cudaMemcpyDeviceToHost, st));
+    if (visits) CUDA_TRY(cudaMemcpyAsync(visits, h->visits_dev, sizeof(int32_t) * (size_t)n * stride, cudaMemcpyDeviceToHost, st));
+    if (value_sums) CUDA_TRY(cudaMemcpyAsync(value_sums, h->wsum_dev, sizeof(double) * (size_t)n * stride, cudaMemcpyDeviceToHost, st));
+    if (moves) CUDA_TRY(cudaMemcpyAsync(moves, h->moves_dev, sizeof(zc_chess_move) * (size_t)n * stride, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    for (int i = 0; i < n; ++i)
+        if (results[i].status != 0) return fail(ZC_ECAPACITY, "tree " + std::to_string(i) + " outgrew its arena");
+    return ZC_OK;
+}
+
+extern "C" int zc_search_tree_hash(zc_search* h, uint64_t* host_hashes, void* stream) {
+    if (int rc = check_handle(h)) return rc;
+    if (!host_hashes || h->n_trees < 1) return fail(ZC_EINVAL, "tree_hash: bad arguments");
+    CUDA_TRY(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    k_tree_hash<C4Game><<<(h->n_trees + 63) / 64, 64, 0, st>>>(h->arena, h->arena_slots, h->n_trees, h->hash_dev);
+    h->launches++;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(host_hashes, h->hash_dev, sizeof(uint64_t) * h->n_trees, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return ZC_OK;
+}
+
+extern "C" int zc_search_get_counters(zc_search* h, zc_search_counters* out, void* stream) {
+    if (int rc = check_handle(h)) return rc;
+    if (!out) return fail(ZC_EINVAL, "out is NULL");
+    memset(out, 0, sizeof *out);
+    out->kernel_launches = h->launches;
+    if (h->n_trees < 1) return ZC_OK;
+    CUDA_TRY(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    std::vector<TreeCtl> c((size_t)h->n_trees);
+    CUDA_TRY(cudaMemcpyAsync(c.data(), h->ctl, sizeof(TreeCtl) * c.size(), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    for (const TreeCtl& t : c) {
+        out->simulations += t.sims_done;
+        out->nodes += t.nodes;
+        out->sum_leaf_depth += (int64_t)t.sum_leaf_depth;
+        out->sum_path_children += (int64_t)t.sum_path_children;
+        out->arena_slots_used += t.top;
+    }
+    return ZC_OK;
+}

@@ -1,0 +1,34 @@
+// Shared helpers for host+device code of libzc_b200.so
+#pragma once
+#include <stdint.h>
+
+#ifdef __CUDACC__
+#define ZC_HD __host__ __device__ __forceinline__
+#define ZC_D __device__ __forceinline__
+#else
+#define ZC_HD inline
+#define ZC_D inline
+#endif
+
+ZC_HD int zc_popc64(uint64_t v) {
+#ifdef __CUDA_ARCH__
+    return __popcll(v);
+#else
+    return __builtin_popcountll(v);
+#endif
+}
+ZC_HD int zc_popc32(uint32_t v) {
+#ifdef __CUDA_ARCH__
+    return __popc(v);
+#else
+    return __builtin_popcount(v);
+#endif
+}
+// index of the lowest set bit (v != 0)
+ZC_HD int zc_ctz64(uint64_t v) {
+#ifdef __CUDA_ARCH__
+    return __ffsll((long long)v) - 1;
+#else
+    return __builtin_ctzll(v);
+#endif
+}

@@ -1,0 +1,152 @@
+"""Thin Python wrapper of the zc_search C-ABI handle: thousands of MCTS trees on one GPU.
+
+This is the batched replacement of `engine.mcts.get_move` (engine/mcts/src/mcts.cpp:102-160,
+bindings_mcts.cpp:9-11): one `TreeSearch` holds the node arenas of up to `max_trees` trees and
+`run()` advances all of them.  Nothing here computes on the CPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import _ffi
+from ._ffi import (C4_STATE_DTYPE, CHESS_MOVE_DTYPE, CHESS_STATE_DTYPE, EVAL_C4_POSITIONAL, EVAL_C4_TERMINAL,
+                   EVAL_CHESS_CRUDE, EVAL_EXTERNAL, GAME_C4, GAME_CHESS, POLICY_FIRST, POLICY_LAST, POLICY_RANDOM,
+                   ROOT_RESULT_DTYPE, check, lib)
+
+__all__ = ["TreeSearch", "c4_pack_rows", "c4_pack_cols", "c4_unpack_rows"]
+
+
+def _ptr(a: Optional[np.ndarray]):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _stream_ptr(stream) -> Optional[int]:
+    if stream is None:
+        return None
+    if isinstance(stream, int):
+        return stream or None
+    return int(stream.cuda_stream) or None  # torch.cuda.Stream
+
+
+class TreeSearch:
+    def __init__(self, game: int, max_trees: int, max_sims: int, device: int = 0, arena_slots_per_tree: int = 0):
+        self._h = C.c_void_p()
+        self.game, self.max_trees, self.max_sims, self.device = game, max_trees, max_sims, device
+        check(lib().zc_search_create(game, device, max_trees, max_sims, arena_slots_per_tree, C.byref(self._h)))
+        self.n_trees = 0
+        self.state_dtype = C4_STATE_DTYPE if game == GAME_C4 else CHESS_STATE_DTYPE
+        self.max_moves = 7 if game == GAME_C4 else _ffi.MAX_MOVES
+
+    def close(self) -> None:
+        if self._h:
+            lib().zc_search_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def device_bytes(self) -> int:
+        return int(lib().zc_search_device_bytes(self._h))
+
+    # -- roots ---------------------------------------------------------------------------------
+    def set_roots(self, states: np.ndarray, stream=None) -> None:
+        """states: structured array (C4_STATE_DTYPE / CHESS_STATE_DTYPE) in host memory."""
+        states = np.ascontiguousarray(states, dtype=self.state_dtype)
+        check(lib().zc_search_set_roots(self._h, _ptr(states), len(states), _stream_ptr(stream)))
+        self.n_trees = len(states)
+
+    def set_roots_dev(self, dev_ptr: int, n: int, stream=None) -> None:
+        check(lib().zc_search_set_roots_dev(self._h, C.c_void_p(dev_ptr), n, _stream_ptr(stream)))
+        self.n_trees = n
+
+    # -- fused search with a built-in evaluator ------------------------------------------------
+    def run(self, simulations: int, c: float = 1.4, batch_size: int = 32, evaluator: int = EVAL_C4_TERMINAL,
+            policy: int = POLICY_FIRST, seed: int = 0, stream=None) -> None:
+        check(lib().zc_search_run(self._h, simulations, float(c), batch_size, evaluator, policy, seed, _stream_ptr(stream)))
+
+    # -- split phase for an external (neural) evaluator -----------------------------------------
+    def begin(self, simulations: int, c: float = 1.4, batch_size: int = 32, policy: int = POLICY_FIRST, seed: int = 0):
+        check(lib().zc_search_begin(self._h, simulations, float(c), batch_size, policy, seed))
+
+    def pending(self) -> int:
+        return int(lib().zc_search_pending(self._h))
+
+    def select(self, planes_ptr: int, plane_dtype: int = _ffi.PLANE_BF16, stream=None) -> None:
+        check(lib().zc_search_select(self._h, C.c_void_p(planes_ptr), plane_dtype, _stream_ptr(stream)))
+
+    def backprop(self, values_ptr: int, stream=None) -> None:
+        check(lib().zc_search_backprop(self._h, C.c_void_p(values_ptr), _stream_ptr(stream)))
+
+    # -- readout ---------------------------------------------------------------------------------
+    def results(self, stats: bool = True, stream=None) -> dict:
+        n = self.n_trees
+        res = np.zeros(n, dtype=ROOT_RESULT_DTYPE)
+        visits = wsum = moves = None
+        stride = self.max_moves
+        if stats:
+            visits = np.zeros((n, stride), dtype=np.int32)
+            wsum = np.zeros((n, stride), dtype=np.float64)
+            moves = np.zeros((n, stride), dtype=CHESS_MOVE_DTYPE)
+        check(lib().zc_search_results(self._h, _ptr(res), _ptr(visits), _ptr(wsum), _ptr(moves), stride, _stream_ptr(stream)))
+        return {"result": res, "visits": visits, "value_sums": wsum, "moves": moves}
+
+    def tree_hash(self, stream=None) -> np.ndarray:
+        out = np.zeros(self.n_trees, dtype=np.uint64)
+        check(lib().zc_search_tree_hash(self._h, _ptr(out), _stream_ptr(stream)))
+        return out
+
+    def counters(self, stream=None) -> dict:
+        c = _ffi.Counters()
+        check(lib().zc_search_get_counters(self._h, C.byref(c), _stream_ptr(stream)))
+        return {k: int(getattr(c, k)) for k, _ in c._fields_}
+
+
+# ------------------------------------------------------------------------------------ C4 packing
+def c4_pack_rows(rows: Sequence[Sequence[str]], turn: int) -> tuple:
+    """6x7 board of ' '/'X'/'O' (row 0 = top, c4_backend.py:11-12) -> (x_bits, o_bits, turn)."""
+    x = o = 0
+    for r in range(6):
+        for c in range(7):
+            cell = rows[r][c]
+            if cell == 'X':
+                x |= 1 << (c * 7 + (5 - r))
+            elif cell == 'O':
+                o |= 1 << (c * 7 + (5 - r))
+    return x, o, turn
+
+
+def c4_unpack_rows(x: int, o: int) -> list:
+    rows = [[' '] * 7 for _ in range(6)]
+    for r in range(6):
+        for c in range(7):
+            b = 1 << (c * 7 + (5 - r))
+            if x & b:
+                rows[r][c] = 'X'
+            elif o & b:
+                rows[r][c] = 'O'
+    return rows
+
+
+def c4_pack_cols(cols: Sequence[int]) -> tuple:
+    """Position after playing `cols` from the empty board (X first)."""
+    x = o = 0
+    turn = 0
+    for c in cols:
+        occ = x | o
+        for h in range(6):
+            b = 1 << (c * 7 + h)
+            if not occ & b:
+                if turn == 0:
+                    x |= b
+                else:
+                    o |= b
+                break
+        turn = 1 - turn
+    return x, o, turn
