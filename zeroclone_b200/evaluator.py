@@ -1,0 +1,86 @@
+"""Batched neural leaf evaluation: the `network_latest` / `network_at_path` modes of the
+reference's Value class (engine/value_functions.py:61-129) without the worker thread and the
+per-state queues -- every tree's pending leaves are already one contiguous device batch, so the
+evaluation is ONE forward per search batch.
+
+The forward is PyTorch (cuDNN/cuBLAS tensor-core kernels): it is the one dense contraction of
+the path.  BatchNorm (eval mode, network.py:15,18,30) is folded into the convolution weights in
+fp32 before the cast to the compute dtype.
+"""
+from __future__ import annotations
+
+from typing import List, Tuple
+
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+
+def _fold(conv: nn.Conv2d, bn: nn.BatchNorm2d) -> Tuple[torch.Tensor, torch.Tensor]:
+    w = conv.weight.detach().float()
+    scale = bn.weight.detach().float() / torch.sqrt(bn.running_var.detach().float() + bn.eps)
+    b = bn.bias.detach().float() - bn.running_mean.detach().float() * scale
+    if conv.bias is not None:
+        b = b + conv.bias.detach().float() * scale
+    return w * scale.view(-1, 1, 1, 1), b
+
+
+class NetEvaluator:
+    """values = tanh(head(res(stem(planes))))  for planes[B, C, H, W] in `dtype`; returns float32[B]."""
+
+    def __init__(self, model: nn.Module, device="cuda", dtype: torch.dtype = torch.bfloat16, chunk: int = 32768,
+                 residual_fp32: bool = False):
+        model = model.eval()
+        self.device = torch.device(device)
+        self.dtype = dtype
+        self.chunk = chunk
+        self.residual_fp32 = residual_fp32
+        self.in_planes = model.stem[0].in_channels
+        cl = torch.channels_last
+
+        def prep(w, b):
+            return (w.to(self.device, dtype).contiguous(memory_format=cl), b.to(self.device, dtype))
+
+        self.stem = prep(*_fold(model.stem[0], model.stem[1]))
+        self.blocks: List[tuple] = []
+        for blk in model.res:
+            self.blocks.append(prep(*_fold(blk.seq[0], blk.seq[1])) + prep(*_fold(blk.seq[3], blk.seq[4])))
+        lin = model.head[2]
+        self.lin_w = lin.weight.detach().float().to(self.device).t().contiguous()   # [C, 1]
+        self.lin_b = lin.bias.detach().float().to(self.device)
+        self.flops_per_leaf = None
+
+    @torch.inference_mode()
+    def _forward_chunk(self, planes: torch.Tensor) -> torch.Tensor:
+        x = planes.contiguous(memory_format=torch.channels_last)
+        x = F.relu_(F.conv2d(x, self.stem[0], self.stem[1], padding=1))
+        if self.residual_fp32:
+            r = x.float()
+            for w1, b1, w2, b2 in self.blocks:
+                y = F.relu_(F.conv2d(x, w1, b1, padding=1))
+                y = F.conv2d(y, w2, b2, padding=1)
+                r = F.relu_(r.add_(y))
+                x = r.to(self.dtype)
+            pooled = r.mean(dim=(2, 3))
+        else:
+            for w1, b1, w2, b2 in self.blocks:
+                y = F.relu_(F.conv2d(x, w1, b1, padding=1))
+                y = F.conv2d(y, w2, b2, padding=1)
+                x = F.relu_(y.add_(x))
+            pooled = x.float().mean(dim=(2, 3))
+        return torch.tanh(torch.addmm(self.lin_b, pooled, self.lin_w)).view(-1)
+
+    @torch.inference_mode()
+    def __call__(self, planes: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+        n = planes.shape[0]
+        if out is None:
+            out = torch.empty(n, dtype=torch.float32, device=planes.device)
+        for s in range(0, n, self.chunk):
+            out[s:s + self.chunk] = self._forward_chunk(planes[s:s + self.chunk])
+        return out
+
+
+def tower_flops_per_leaf(in_planes: int, h: int, w: int, channels: int = 128, blocks: int = 8) -> float:
+    """2*MACs of one forward: stem + 2*blocks convs + head."""
+    cells = h * w
+    return 2.0 * (cells * in_planes * channels * 9 + 2 * blocks * cells * channels * channels * 9 + channels)

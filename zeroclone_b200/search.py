@@ -84,6 +84,30 @@ class TreeSearch:
     def backprop(self, values_ptr: int, stream=None) -> None:
         check(lib().zc_search_backprop(self._h, C.c_void_p(values_ptr), _stream_ptr(stream)))
 
+    def run_network(self, evaluator, simulations: int, c: float = 1.4, batch_size: int = 32,
+                    policy: int = POLICY_FIRST, seed: int = 0) -> None:
+        """get_move's loop with a neural evaluator (mcts.cpp:112-127 calling value.batch): per batch
+        one select kernel, one forward over every tree's pending leaves, one backprop kernel.
+        `evaluator(planes[B,C,H,W], out=values[B])` is any callable on device tensors (NetEvaluator)."""
+        import torch
+
+        dev = torch.device("cuda", self.device)
+        dtype = getattr(evaluator, "dtype", torch.float32)
+        code = {torch.bfloat16: _ffi.PLANE_BF16, torch.float32: _ffi.PLANE_F32, torch.float16: _ffi.PLANE_F16}[dtype]
+        shape = (self.n_trees * batch_size,) + ((2, 6, 7) if self.game == GAME_C4 else (17, 8, 8))
+        key = (shape, dtype)
+        if getattr(self, "_planes_key", None) != key:
+            self._planes = torch.empty(shape, dtype=dtype, device=dev)
+            self._values = torch.empty(shape[0], dtype=torch.float32, device=dev)
+            self._planes_key = key
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream().cuda_stream
+            self.begin(simulations, c, batch_size, policy, seed)
+            while self.pending() > 0:
+                self.select(self._planes.data_ptr(), code, stream)
+                evaluator(self._planes, out=self._values)
+                self.backprop(self._values.data_ptr(), stream)
+
     # -- readout ---------------------------------------------------------------------------------
     def results(self, stats: bool = True, stream=None) -> dict:
         n = self.n_trees
