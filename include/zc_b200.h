@@ -118,7 +118,7 @@ int zc_c4_get_move_order(uint8_t *table /* [128][8] */);
 /* ---- search handle: replaces get_move() for a whole batch of trees ----------------------- */
 
 /* arena_slots_per_tree: 16-byte slots per tree, 0 = default (C4: exact worst case;
- * chess: (max_sims+1) * 48).  Memory = max_trees * arena_slots_per_tree * 16 B. */
+ * chess: (max_sims+1) * 72).  Memory = max_trees * arena_slots_per_tree * 16 B. */
 int zc_search_create(int game, int device, int max_trees, int max_sims, int64_t arena_slots_per_tree,
                      zc_search **out);
 int zc_search_destroy(zc_search *h);
@@ -173,6 +173,40 @@ typedef struct zc_search_counters {
     int64_t kernel_launches;   /* kernels launched by this handle since creation */
 } zc_search_counters;
 int zc_search_get_counters(zc_search *h, zc_search_counters *out, void *stream);
+
+/* ---- game rules: the six-function backend interface (engine/README.md:13-28) --------------- */
+
+/* Single-state helpers for the Python backend shims (root bookkeeping of Engine.play_move /
+ * legal_moves / _evaluate, engine.py:94-108,148-157).  They run the same host+device rule code as
+ * the kernels, on the host, one state at a time; they are not a fallback for the search. */
+int zc_c4_init_state(zc_c4_state *out);                                    /* c4_backend.py:11-12 */
+int zc_c4_legal_moves(const zc_c4_state *s, int32_t *cols /* [7] */);      /* :49-50, returns count, set order */
+int zc_c4_play_move(const zc_c4_state *s, int col, zc_c4_state *out);      /* :14-23 */
+int zc_c4_check_win(const zc_c4_state *s);                                 /* :25-44, 0/1 */
+int zc_c4_check_draw(const zc_c4_state *s);                                /* :46-47, 0/1 */
+int zc_c4_to_tensor(const zc_c4_state *s, float *out /* [2][6][7] */);     /* :52-61 */
+
+int zc_chess_init_state(zc_chess_state *out);                              /* chess_backend.cpp:445-457 */
+int zc_chess_from_fen(const char *fen, zc_chess_state *out);               /* :525-556 */
+int zc_chess_legal_moves(const zc_chess_state *s, zc_chess_move *out /* [ZC_MAX_MOVES] */); /* :184-360, returns count */
+int zc_chess_play_move(const zc_chess_state *s, const zc_chess_move *m, zc_chess_state *out); /* :364-400 */
+int zc_chess_check_win(const zc_chess_state *s);                           /* :404-412 */
+/* hist_*: the side's moves, most recent first (state.h:14, chess_backend.cpp:374) */
+int zc_chess_check_draw(const zc_chess_state *s, const zc_chess_move *hist_white, int n_white,
+                        const zc_chess_move *hist_black, int n_black);     /* :416-441 */
+int zc_chess_to_tensor(const zc_chess_state *s, float *out /* [17][8][8] */); /* :461-521 */
+
+/* Batched rules ON THE DEVICE (the kernels the search uses), host buffers in and out:
+ * moves[n][ZC_MAX_MOVES], counts[n], flags[n]: bit 0 = check_win, bit 1 = no moves and not in check
+ * (the stalemate branch of check_draw), bit 2 = side to move in check. */
+int zc_chess_legal_moves_batch(int device, const zc_chess_state *states, int n, zc_chess_move *moves,
+                               int32_t *counts, int32_t *flags);
+/* perft as the reference's rules count it (number of legal moves at the last ply), breadth-first
+ * on the device */
+int zc_chess_perft(int device, const zc_chess_state *root, int depth, uint64_t *out);
+/* C4 on the device: per state the ordered legal columns (255-padded to 8), flags bit 0 = check_win,
+ * bit 1 = check_draw */
+int zc_c4_rules_batch(int device, const zc_c4_state *states, int n, uint8_t *cols /* [n][8] */, int32_t *flags);
 
 #ifdef __cplusplus
 }

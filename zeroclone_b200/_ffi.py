@@ -87,6 +87,19 @@ def lib() -> C.CDLL:
     L.zc_search_results.argtypes = [vp, vp, vp, vp, vp, i32, vp]
     L.zc_search_tree_hash.argtypes = [vp, vp, vp]
     L.zc_search_get_counters.argtypes = [vp, vp, vp]
+    for name in ("zc_c4_init_state", "zc_c4_check_win", "zc_c4_check_draw", "zc_chess_init_state", "zc_chess_check_win"):
+        getattr(L, name).argtypes = [vp]
+    L.zc_c4_legal_moves.argtypes = [vp, vp]
+    L.zc_c4_play_move.argtypes = [vp, i32, vp]
+    L.zc_c4_to_tensor.argtypes = [vp, vp]
+    L.zc_chess_from_fen.argtypes = [C.c_char_p, vp]
+    L.zc_chess_legal_moves.argtypes = [vp, vp]
+    L.zc_chess_play_move.argtypes = [vp, vp, vp]
+    L.zc_chess_check_draw.argtypes = [vp, vp, i32, vp, i32]
+    L.zc_chess_to_tensor.argtypes = [vp, vp]
+    L.zc_chess_legal_moves_batch.argtypes = [i32, vp, i32, vp, vp, vp]
+    L.zc_chess_perft.argtypes = [i32, vp, i32, vp]
+    L.zc_c4_rules_batch.argtypes = [i32, vp, i32, vp, vp]
     assert C.sizeof(RootResult) == ROOT_RESULT_DTYPE.itemsize == 48, (C.sizeof(RootResult), ROOT_RESULT_DTYPE.itemsize)
     assert C.sizeof(C4State) == C4_STATE_DTYPE.itemsize == 24
     assert C.sizeof(ChessState) == CHESS_STATE_DTYPE.itemsize == 72

@@ -11,6 +11,9 @@ struct C4Game {
     static constexpr int SS = 1;            // state slots per node
     static constexpr int FIRST_SLOTS = 9;   // header + state + up to 7 edges: the whole node in one warp load
     static constexpr int PLANE_ELEMS = 84;  // 2 x 6 x 7 (c4_backend.py:52-61)
+    static constexpr int MOVE_SCRATCH = 0;
+    struct Ctx {};
+    ZC_D static Ctx make_ctx(const SearchParams&, unsigned, int) { return Ctx(); }
 
     ZC_D static State state_from_lanes(const uint4& v) {
         const uint4 s = shfl4(v, 1);
@@ -36,13 +39,13 @@ struct C4Game {
         return r;
     }
     ZC_HD static int move_slots(int) { return 0; }                    // moves are implied by the legal mask
-    ZC_HD static void store_moves(uint4*, const State&, uint32_t, int) {}
+    ZC_HD static void store_moves(Ctx&, uint4*, int) {}
     // state after the ei-th move (backend order) of `parent`
     ZC_HD static State child(const State& parent, uint32_t, const uint4*, int, int ei, uint32_t& cmisc) {
         cmisc = 0;
         return c4::play(parent, c4::move_col(c4::legal_mask(parent), ei));
     }
-    ZC_HD static int count_moves(const State& s, uint32_t) { return c4::n_moves(s); }
+    ZC_HD static int count_moves(Ctx&, const State& s, uint32_t) { return c4::n_moves(s); }
     ZC_HD static double eval(const State& s, uint32_t, int evaluator) {
         return evaluator == ZC_EVAL_C4_POSITIONAL ? c4::eval_positional(s) : c4::eval_terminal(s);
     }

@@ -1,0 +1,108 @@
+// Chess plugged into the generic search (search.cuh).
+#pragma once
+#include "chess_rules.cuh"
+#include "search.cuh"
+#include "../../include/zc_b200.h"
+
+namespace zc {
+
+struct ChessGame {
+    using State = chess::Board;
+    static constexpr int SS = 2;             // four bit planes = 32 bytes
+    static constexpr int FIRST_SLOTS = 32;   // header + state + first 29 edges in one warp load
+    static constexpr int PLANE_ELEMS = 17 * 64;
+    static constexpr int MOVE_SCRATCH = 224; // >= 218 moves, multiple of 8
+
+    struct Ctx {
+        uint16_t* moves;   // this lane's move buffer
+    };
+    ZC_D static Ctx make_ctx(const SearchParams& p, unsigned warp_slot, int lane) {
+        Ctx c;
+        c.moves = p.scratch + ((size_t)warp_slot * 32 + (size_t)lane) * MOVE_SCRATCH;
+        return c;
+    }
+    ZC_D static State state_from_lanes(const uint4& v) {
+        const uint4 a = shfl4(v, 1), b = shfl4(v, 2);
+        State s;
+        s.p0 = ((uint64_t)a.y << 32) | a.x;
+        s.p1 = ((uint64_t)a.w << 32) | a.z;
+        s.p2 = ((uint64_t)b.y << 32) | b.x;
+        s.p3 = ((uint64_t)b.w << 32) | b.z;
+        return s;
+    }
+    ZC_HD static void store_state(uint4* dst, const State& s) {
+        dst[0] = make_uint4((uint32_t)s.p0, (uint32_t)(s.p0 >> 32), (uint32_t)s.p1, (uint32_t)(s.p1 >> 32));
+        dst[1] = make_uint4((uint32_t)s.p2, (uint32_t)(s.p2 >> 32), (uint32_t)s.p3, (uint32_t)(s.p3 >> 32));
+    }
+    ZC_HD static State load_state(const uint4* src) {
+        const uint4 a = src[0], b = src[1];
+        State s;
+        s.p0 = ((uint64_t)a.y << 32) | a.x;
+        s.p1 = ((uint64_t)a.w << 32) | a.z;
+        s.p2 = ((uint64_t)b.y << 32) | b.x;
+        s.p3 = ((uint64_t)b.w << 32) | b.z;
+        return s;
+    }
+    ZC_D static State shfl_state(const State& s, int src) {
+        State r;
+        r.p0 = __shfl_sync(FULL_MASK, s.p0, src);
+        r.p1 = __shfl_sync(FULL_MASK, s.p1, src);
+        r.p2 = __shfl_sync(FULL_MASK, s.p2, src);
+        r.p3 = __shfl_sync(FULL_MASK, s.p3, src);
+        return r;
+    }
+    ZC_HD static int move_slots(int k) { return (k + 7) >> 3; }
+    // packed move i of the node at `node` (k moves): stored after the edges, 8 per slot
+    ZC_HD static uint16_t move_at(const uint4* node, int k, int i) {
+        const uint16_t* mv = reinterpret_cast<const uint16_t*>(node + 1 + SS + k);
+        return mv[i];
+    }
+    ZC_HD static State child(const State& parent, uint32_t pmisc, const uint4* pnode, int pk, int ei, uint32_t& cmisc) {
+        const uint16_t m = move_at(pnode, pk, ei);
+        return chess::play(parent, pmisc, chess::move_from(m), chess::move_to(m), cmisc);
+    }
+    ZC_HD static int count_moves(Ctx& gx, const State& s, uint32_t misc) {
+        return chess::generate(s, (int)(misc & chess::MISC_TURN), gx.moves);
+    }
+    ZC_HD static void store_moves(Ctx& gx, uint4* dst, int k) {
+        const uint4* src = reinterpret_cast<const uint4*>(gx.moves);
+        for (int i = 0; i < move_slots(k); ++i) dst[i] = src[i];
+    }
+    ZC_HD static double eval(const State& s, uint32_t misc, int) { return chess::crude_score(s, (int)(misc & 1u), 0); }
+    ZC_HD static double eval_child(const State& s, uint32_t misc, int k, int) { return chess::crude_score(s, (int)(misc & 1u), k); }
+
+    // chess_backend.cpp:461-521 -- 17 planes x 64 cells; planes 0-11 'PNBRQKpnbrqk', 12 white to move,
+    // 13-16 castling flags.  Cell order r*8+c = bit order of the boards.
+    ZC_HD static uint64_t plane_bits(const State& s, uint32_t misc, int pl) {
+        if (pl < 12) {
+            const uint64_t t = chess::of_type(s, pl % 6 + 1);
+            return t & (pl < 6 ? ~s.p3 : s.p3) & chess::occupied(s);
+        }
+        const bool on = pl == 12 ? !(misc & chess::MISC_TURN) : (misc >> (pl - 12)) & 1u;
+        return on ? ~0ull : 0ull;
+    }
+    ZC_D static void pack_planes(void* planes, int dtype, size_t row, bool valid, bool in_range, const State& s, uint32_t misc) {
+        if (!in_range) return;
+        const uint32_t one16 = dtype == 2 ? 0x3C00u : 0x3F80u;
+#pragma unroll 1
+        for (int pl = 0; pl < 17; ++pl) {
+            const uint64_t bb = valid ? plane_bits(s, misc, pl) : 0ull;
+#pragma unroll 1
+            for (int q = 0; q < 16; ++q) {
+                const uint32_t bits = (uint32_t)(bb >> (4 * q)) & 0xFu;
+                const size_t o = (row * 17 + pl) * 16 + q;
+                if (dtype == 1) {
+                    reinterpret_cast<float4*>(planes)[o] =
+                        make_float4(bits & 1 ? 1.f : 0.f, bits & 2 ? 1.f : 0.f, bits & 4 ? 1.f : 0.f, bits & 8 ? 1.f : 0.f);
+                } else {
+                    uint2 h;
+                    h.x = (bits & 1 ? one16 : 0u) | (bits & 2 ? one16 << 16 : 0u);
+                    h.y = (bits & 4 ? one16 : 0u) | (bits & 8 ? one16 << 16 : 0u);
+                    reinterpret_cast<uint2*>(planes)[o] = h;
+                }
+            }
+        }
+    }
+};
+
+}  // namespace zc

@@ -1,0 +1,284 @@
+// Chess rules on bitboards -- host+device.
+// Semantics (including every deviation from FIDE chess) follow the reference's
+// engine/games/chess/src/chess_backend.cpp, cited per function; the representation does not:
+// the reference scans a 64-byte mailbox, this keeps four bit planes of 4-bit piece codes and
+// derives attack sets with branch-free Kogge-Stone fills, emitting moves in the reference's
+// scan order (square 0..63, then its per-piece direction order, rays outward) because move
+// order is part of the search result (mcts.cpp:57,154 break ties by index).
+//
+// Square i = r*8+c, r = 0 is rank 8 (chess_backend.cpp:445-457); white moves toward r = 0.
+#pragma once
+#include <stdint.h>
+
+#include "zc_common.cuh"
+
+namespace zc {
+namespace chess {
+
+// piece code: bits 0-2 type (1 P, 2 N, 3 B, 4 R, 5 Q, 6 K), bit 3 = black, 0 = empty
+enum { PAWN = 1, KNIGHT = 2, BISHOP = 3, ROOK = 4, QUEEN = 5, KING = 6 };
+
+struct Board {
+    uint64_t p0, p1, p2, p3;   // bit planes of the piece code
+};
+// misc byte carried in the node header: bit 0 turn (0 white), bits 1-4 w_ck, w_cq, b_ck, b_cq
+// (state.h:11-13).  The castling flags only feed state_to_tensor; castling is never generated.
+constexpr uint32_t MISC_TURN = 1u, MISC_WCK = 2u, MISC_WCQ = 4u, MISC_BCK = 8u, MISC_BCQ = 16u;
+
+constexpr uint64_t FILE_A = 0x0101010101010101ull, FILE_H = 0x8080808080808080ull;
+
+ZC_HD uint64_t bit(int sq) { return 1ull << sq; }
+ZC_HD uint64_t occupied(const Board& b) { return b.p0 | b.p1 | b.p2; }
+ZC_HD uint64_t of_type(const Board& b, int t) {
+    return ((t & 1) ? b.p0 : ~b.p0) & ((t & 2) ? b.p1 : ~b.p1) & ((t & 4) ? b.p2 : ~b.p2);
+}
+ZC_HD uint64_t of_side(const Board& b, int side) { return occupied(b) & (side ? b.p3 : ~b.p3); }
+ZC_HD int piece_at(const Board& b, int sq) {
+    return (int)(((b.p0 >> sq) & 1) | (((b.p1 >> sq) & 1) << 1) | (((b.p2 >> sq) & 1) << 2) | (((b.p3 >> sq) & 1) << 3));
+}
+ZC_HD void put_piece(Board& b, int sq, int code) {
+    const uint64_t m = ~bit(sq);
+    b.p0 = (b.p0 & m) | ((uint64_t)(code & 1) << sq);
+    b.p1 = (b.p1 & m) | ((uint64_t)((code >> 1) & 1) << sq);
+    b.p2 = (b.p2 & m) | ((uint64_t)((code >> 2) & 1) << sq);
+    b.p3 = (b.p3 & m) | ((uint64_t)((code >> 3) & 1) << sq);
+}
+ZC_HD int code_of_char(uint8_t ch) {
+    switch (ch) {
+    case 'P': return 1;  case 'N': return 2;  case 'B': return 3;  case 'R': return 4;  case 'Q': return 5;  case 'K': return 6;
+    case 'p': return 9;  case 'n': return 10; case 'b': return 11; case 'r': return 12; case 'q': return 13; case 'k': return 14;
+    default: return 0;   // ' ' or 0 (chess_backend.cpp:40-43); any other byte is treated as empty
+    }
+}
+ZC_HD uint8_t char_of_code(int code) {
+    const char* t = " PNBRQK  pnbrqk ";
+    return (uint8_t)t[code & 15];
+}
+// captured-piece value attached to a move (chess_backend.cpp:50-64)
+ZC_HD int capture_value(int code) {
+    switch (code & 7) {
+    case PAWN: return 1;  case KNIGHT: case BISHOP: return 3;  case ROOK: return 5;  case QUEEN: return 9;  case KING: return 100;
+    default: return 0;
+    }
+}
+
+// ---- Kogge-Stone occluded fill along one direction.  kLeft: shift toward higher indices.
+template <int kShift, bool kLeft>
+ZC_HD uint64_t shift_dir(uint64_t x) { return kLeft ? (x << kShift) : (x >> kShift); }
+// squares reachable from `from` along the direction until and including the first blocker
+template <int kShift, bool kLeft>
+ZC_HD uint64_t ray(uint64_t from, uint64_t empty, uint64_t wrap) {
+    uint64_t gen = from, pro = empty & wrap;
+    gen |= pro & shift_dir<kShift, kLeft>(gen);
+    pro &= shift_dir<kShift, kLeft>(pro);
+    gen |= pro & shift_dir<2 * kShift, kLeft>(gen);
+    pro &= shift_dir<2 * kShift, kLeft>(pro);
+    gen |= pro & shift_dir<4 * kShift, kLeft>(gen);
+    return shift_dir<kShift, kLeft>(gen) & wrap;
+}
+// direction ids in the reference's queen_dirs order (chess_backend.cpp:27-30):
+//   0 (-1,-1)  1 (-1,+1)  2 (+1,-1)  3 (+1,+1)  4 (-1,0)  5 (+1,0)  6 (0,-1)  7 (0,+1)
+ZC_HD uint64_t ray_dir(int d, uint64_t from, uint64_t empty) {
+    switch (d) {
+    case 0: return ray<9, false>(from, empty, ~FILE_H);
+    case 1: return ray<7, false>(from, empty, ~FILE_A);
+    case 2: return ray<7, true>(from, empty, ~FILE_H);
+    case 3: return ray<9, true>(from, empty, ~FILE_A);
+    case 4: return ray<8, false>(from, empty, ~0ull);
+    case 5: return ray<8, true>(from, empty, ~0ull);
+    case 6: return ray<1, false>(from, empty, ~FILE_H);
+    default: return ray<1, true>(from, empty, ~FILE_A);
+    }
+}
+ZC_HD bool dir_ascending(int d) { return d == 2 || d == 3 || d == 5 || d == 7; }
+ZC_HD uint64_t diag_attacks(uint64_t from, uint64_t empty) {
+    return ray<9, false>(from, empty, ~FILE_H) | ray<7, false>(from, empty, ~FILE_A) | ray<7, true>(from, empty, ~FILE_H) |
+           ray<9, true>(from, empty, ~FILE_A);
+}
+ZC_HD uint64_t orth_attacks(uint64_t from, uint64_t empty) {
+    return ray<8, false>(from, empty, ~0ull) | ray<8, true>(from, empty, ~0ull) | ray<1, false>(from, empty, ~FILE_H) |
+           ray<1, true>(from, empty, ~FILE_A);
+}
+ZC_HD uint64_t knight_attacks(uint64_t b) {
+    const uint64_t l1 = (b >> 1) & ~FILE_H, l2 = (b >> 2) & ~(FILE_H | (FILE_H >> 1));
+    const uint64_t r1 = (b << 1) & ~FILE_A, r2 = (b << 2) & ~(FILE_A | (FILE_A << 1));
+    const uint64_t h1 = l1 | r1, h2 = l2 | r2;
+    return (h1 << 16) | (h1 >> 16) | (h2 << 8) | (h2 >> 8);
+}
+ZC_HD uint64_t king_attacks(uint64_t b) {
+    const uint64_t h = ((b >> 1) & ~FILE_H) | ((b << 1) & ~FILE_A), row = h | b;
+    return h | (row << 8) | (row >> 8);
+}
+
+// chess_backend.cpp:85-144 -- is the king of `side` on square ksq attacked, given the enemy sets?
+ZC_HD bool square_attacked(int side, int ksq, uint64_t occ, uint64_t e_pawn, uint64_t e_knight, uint64_t e_diag,
+                           uint64_t e_orth, uint64_t e_king) {
+    const uint64_t k = bit(ksq);
+    // pawns: a white king looks one row up (r-1) for 'p', a black king one row down for 'P'
+    const uint64_t pawn_from = side == 0 ? (((k >> 9) & ~FILE_H) | ((k >> 7) & ~FILE_A))
+                                         : (((k << 7) & ~FILE_H) | ((k << 9) & ~FILE_A));
+    if (pawn_from & e_pawn) return true;
+    if (knight_attacks(k) & e_knight) return true;
+    if (king_attacks(k) & e_king) return true;
+    const uint64_t empty = ~occ;
+    if (e_orth && (orth_attacks(k, empty) & e_orth)) return true;
+    if (e_diag && (diag_attacks(k, empty) & e_diag)) return true;
+    return false;
+}
+
+struct Sets {   // derived once per position
+    uint64_t occ, own, enemy, e_pawn, e_knight, e_bishop, e_rook, e_queen, e_king, own_king;
+};
+ZC_HD Sets derive(const Board& b, int turn) {
+    Sets s;
+    s.occ = occupied(b);
+    s.own = of_side(b, turn);
+    s.enemy = s.occ & ~s.own;
+    s.e_pawn = of_type(b, PAWN) & s.enemy;
+    s.e_knight = of_type(b, KNIGHT) & s.enemy;
+    s.e_bishop = of_type(b, BISHOP) & s.enemy;
+    s.e_rook = of_type(b, ROOK) & s.enemy;
+    s.e_queen = of_type(b, QUEEN) & s.enemy;
+    s.e_king = of_type(b, KING) & s.enemy;
+    s.own_king = of_type(b, KING) & s.own;
+    return s;
+}
+
+// chess_backend.cpp:345-358 -- make the move, find the mover's (first) king, test it.
+// A side without a king is never "in check" (the reference reads out of range there).
+ZC_HD bool move_keeps_king_safe(const Sets& s, int turn, int from, int to, bool king_moves) {
+    const uint64_t f = bit(from), t = bit(to);
+    const uint64_t kings = king_moves ? ((s.own_king & ~f) | t) : s.own_king;
+    if (!kings) return true;
+    const int ksq = zc_ctz64(kings);
+    const uint64_t occ = (s.occ & ~f) | t, keep = ~t;
+    return !square_attacked(turn, ksq, occ, s.e_pawn & keep, s.e_knight & keep, (s.e_bishop | s.e_queen) & keep,
+                            (s.e_rook | s.e_queen) & keep, s.e_king & keep);
+}
+ZC_HD bool in_check(const Board& b, int turn) {   // king of the side to move attacked now?
+    const Sets s = derive(b, turn);
+    if (!s.own_king) return false;
+    return square_attacked(turn, zc_ctz64(s.own_king), s.occ, s.e_pawn, s.e_knight, s.e_bishop | s.e_queen,
+                           s.e_rook | s.e_queen, s.e_king);
+}
+
+// chess_backend.cpp:188-198 -- no pawn/rook/queen and at most one minor piece: no moves at all
+ZC_HD bool insufficient_material(const Board& b) {
+    const uint64_t heavy = of_type(b, PAWN) | of_type(b, ROOK) | of_type(b, QUEEN);
+    const uint64_t minor = of_type(b, KNIGHT) | of_type(b, BISHOP);
+    return heavy == 0 && zc_popc64(minor) <= 1;
+}
+
+ZC_HD uint16_t pack_move(int from, int to) { return (uint16_t)(from | (to << 6)); }
+ZC_HD int move_from(uint16_t m) { return m & 63; }
+ZC_HD int move_to(uint16_t m) { return (m >> 6) & 63; }
+
+// chess_backend.cpp:184-360.  Writes the legal moves, in the reference's order, to out[]
+// (if non-null) and returns their number (<= 218).
+ZC_HD int generate(const Board& b, int turn, uint16_t* out) {
+    if (insufficient_material(b)) return 0;
+    const Sets s = derive(b, turn);
+    const uint64_t empty = ~s.occ;
+    const uint64_t targets_ok = ~s.own & ~s.e_king;       // a king is never captured (:240,261,306,331)
+    int n = 0;
+    uint64_t movers = s.own;
+    while (movers) {
+        const int sq = zc_ctz64(movers);
+        movers &= movers - 1;
+        const int type = piece_at(b, sq) & 7, r = sq >> 3, c = sq & 7;
+        const uint64_t me = bit(sq);
+        if (type == PAWN) {                                             // :213-252
+            const int dir = turn == 0 ? -1 : 1, home = turn == 0 ? 6 : 1;
+            const int nr = r + dir;
+            if (nr >= 0 && nr < 8) {
+                const int one = nr * 8 + c;
+                if (empty >> one & 1) {
+                    if (move_keeps_king_safe(s, turn, sq, one, false)) { if (out) out[n] = pack_move(sq, one); ++n; }
+                    const int two = one + dir * 8;
+                    if (r == home && (empty >> two & 1))
+                        if (move_keeps_king_safe(s, turn, sq, two, false)) { if (out) out[n] = pack_move(sq, two); ++n; }
+                }
+                for (int dc = -1; dc <= 1; dc += 2) {
+                    const int cc = c + dc;
+                    if (cc < 0 || cc > 7) continue;
+                    const int t = nr * 8 + cc;
+                    if ((s.enemy & ~s.e_king) >> t & 1)
+                        if (move_keeps_king_safe(s, turn, sq, t, false)) { if (out) out[n] = pack_move(sq, t); ++n; }
+                }
+            }
+        } else if (type == KNIGHT || type == KING) {                    // :255-275, :322-340
+            const bool is_king = type == KING;
+            for (int d = 0; d < 8; ++d) {
+                int dr, dc;
+                if (is_king) {       // king_dirs (:31-34)
+                    dr = d < 4 ? (d < 2 ? -1 : 1) : (d == 4 ? -1 : d == 5 ? 1 : 0);
+                    dc = d < 4 ? ((d & 1) ? 1 : -1) : (d == 6 ? -1 : d == 7 ? 1 : 0);
+                } else {             // knight_dirs (:17-20)
+                    dr = d < 2 ? -2 : d < 4 ? -1 : d < 6 ? 1 : 2;
+                    dc = (d < 2 || d >= 6) ? ((d & 1) ? 1 : -1) : ((d & 1) ? 2 : -2);
+                }
+                const int rr = r + dr, cc = c + dc;
+                if (rr < 0 || rr > 7 || cc < 0 || cc > 7) continue;
+                const int t = rr * 8 + cc;
+                if (!(targets_ok >> t & 1)) continue;
+                if (move_keeps_king_safe(s, turn, sq, t, is_king)) { if (out) out[n] = pack_move(sq, t); ++n; }
+            }
+        } else if (type == BISHOP || type == ROOK || type == QUEEN) {   // :278-319
+            const int d0 = type == ROOK ? 4 : 0, d1 = type == BISHOP ? 4 : 8;
+            for (int d = d0; d < d1; ++d) {
+                uint64_t tg = ray_dir(d, me, empty) & targets_ok;
+                const bool asc = dir_ascending(d);
+                while (tg) {                                            // outward = toward/away from index 0
+                    const int t = asc ? zc_ctz64(tg) : 63 - zc_clz64(tg);
+                    tg &= ~bit(t);
+                    if (move_keeps_king_safe(s, turn, sq, t, false)) { if (out) out[n] = pack_move(sq, t); ++n; }
+                }
+            }
+        }
+    }
+    return n;
+}
+
+// chess_backend.cpp:364-400 on the board planes; flags in/out through `misc`.
+ZC_HD Board play(const Board& b, uint32_t misc, int from, int to, uint32_t& misc_out) {
+    Board n = b;
+    const int pc = piece_at(b, from), fc = from & 7, tc = to & 7, tr = to >> 3;
+    uint32_t m = misc ^ MISC_TURN;
+    if (pc == KING || (pc == ROOK && fc == 7)) m &= ~MISC_WCK;               // :382-385 (any row, as written)
+    if (pc == KING || (pc == ROOK && fc == 0)) m &= ~MISC_WCQ;
+    if (pc == (KING | 8) || (pc == (ROOK | 8) && fc == 7)) m &= ~MISC_BCK;
+    if (pc == (KING | 8) || (pc == (ROOK | 8) && fc == 0)) m &= ~MISC_BCQ;
+    // castling rook hop, only reachable when a two-file king move is fed in (:388-391)
+    if (pc == KING && tc - fc == 2) { put_piece(n, 61, ROOK); put_piece(n, 63, 0); }
+    if (pc == (KING | 8) && tc - fc == 2) { put_piece(n, 5, ROOK | 8); put_piece(n, 7, 0); }
+    if (pc == KING && tc - fc == -2) { put_piece(n, 59, ROOK); put_piece(n, 56, 0); }
+    if (pc == (KING | 8) && tc - fc == -2) { put_piece(n, 3, ROOK | 8); put_piece(n, 0, 0); }
+    int placed = pc;
+    if (tr == 0 && pc == PAWN) placed = QUEEN;                                // :396-397
+    if (tr == 7 && pc == (PAWN | 8)) placed = QUEEN | 8;
+    put_piece(n, to, placed);
+    put_piece(n, from, 0);
+    misc_out = m;
+    return n;
+}
+// does this move reset the fifty-ply counter?  (:380: pawn move or any capture)
+ZC_HD bool resets_fifty(const Board& b, int from, int to) {
+    return (piece_at(b, from) & 7) == PAWN || piece_at(b, to) != 0;
+}
+
+// sum of piece values, white positive (value_functions.py:52-54)
+ZC_HD int material(const Board& b) {
+    const uint64_t w = ~b.p3, k = b.p3;
+    const uint64_t P = of_type(b, PAWN), Nn = of_type(b, KNIGHT) | of_type(b, BISHOP), R = of_type(b, ROOK), Q = of_type(b, QUEEN);
+    return (zc_popc64(P & w) - zc_popc64(P & k)) + 3 * (zc_popc64(Nn & w) - zc_popc64(Nn & k)) +
+           5 * (zc_popc64(R & w) - zc_popc64(R & k)) + 9 * (zc_popc64(Q & w) - zc_popc64(Q & k));
+}
+// crude_chess_score (value_functions.py:49-55) given the number of legal moves of the state:
+// check_win = no moves and king attacked (chess_backend.cpp:404-412) -> +1000 (sic, for the MATED side)
+ZC_HD double crude_score(const Board& b, int turn, int n_moves) {
+    if (n_moves == 0 && in_check(b, turn)) return 1000.0;
+    return (double)((turn ? -1 : 1) * material(b));
+}
+
+}  // namespace chess
+}  // namespace zc

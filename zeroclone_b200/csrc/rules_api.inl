@@ -1,0 +1,350 @@
+// Game-rule entry points of the C-ABI (included by zc_api.cu, same translation unit so that the
+// __constant__ move-order table is shared).
+//   * single-state helpers: host execution of the host+device rule code (root bookkeeping);
+//   * *_batch / perft: the same rule code as device kernels, for parity tests and bulk stepping.
+
+// ------------------------------------------------------------------------------------------ C4 host
+static c4::State c4_rel(const zc_c4_state* s) {
+    c4::State r;
+    r.cur = s->turn == 0 ? s->x : s->o;
+    r.opp = s->turn == 0 ? s->o : s->x;
+    return r;
+}
+
+extern "C" int zc_c4_init_state(zc_c4_state* out) {
+    if (!out) return fail(ZC_EINVAL, "out is NULL");
+    memset(out, 0, sizeof *out);
+    return ZC_OK;
+}
+extern "C" int zc_c4_legal_moves(const zc_c4_state* s, int32_t* cols) {
+    if (!s || !cols) return fail(ZC_EINVAL, "NULL argument");
+    ensure_order();
+    const c4::State r = c4_rel(s);
+    const int mask = c4::legal_mask(r), n = zc_popc32((unsigned)mask);
+    for (int i = 0; i < n; ++i) cols[i] = c4::move_col(mask, i);
+    return n;
+}
+extern "C" int zc_c4_play_move(const zc_c4_state* s, int col, zc_c4_state* out) {
+    if (!s || !out || col < 0 || col > 6) return fail(ZC_EINVAL, "bad argument");
+    const c4::State n = c4::play(c4_rel(s), col);   // n.cur = old opponent, n.opp = mover incl. the new disc
+    zc_c4_state o;
+    memset(&o, 0, sizeof o);
+    o.turn = 1 - s->turn;
+    o.x = s->turn == 0 ? n.opp : n.cur;
+    o.o = s->turn == 0 ? n.cur : n.opp;
+    *out = o;
+    return ZC_OK;
+}
+extern "C" int zc_c4_check_win(const zc_c4_state* s) {
+    if (!s) return fail(ZC_EINVAL, "NULL argument");
+    return c4::check_win(c4_rel(s)) ? 1 : 0;
+}
+extern "C" int zc_c4_check_draw(const zc_c4_state* s) {
+    if (!s) return fail(ZC_EINVAL, "NULL argument");
+    return c4::check_draw(c4_rel(s)) ? 1 : 0;
+}
+extern "C" int zc_c4_to_tensor(const zc_c4_state* s, float* out) {
+    if (!s || !out) return fail(ZC_EINVAL, "NULL argument");
+    const c4::State r = c4_rel(s);
+    for (int row = 0; row < 6; ++row)
+        for (int c = 0; c < 7; ++c) {
+            const int b = c * 7 + (5 - row);
+            out[row * 7 + c] = (float)((r.cur >> b) & 1ull);
+            out[42 + row * 7 + c] = (float)((r.opp >> b) & 1ull);
+        }
+    return ZC_OK;
+}
+
+// ------------------------------------------------------------------------------------------ chess host
+__host__ __device__ static inline chess::Board board_of(const zc_chess_state& s) {
+    chess::Board b = {0, 0, 0, 0};
+    for (int i = 0; i < 64; ++i) chess::put_piece(b, i, chess::code_of_char(s.board[i]));
+    return b;
+}
+__host__ __device__ static inline uint32_t misc_of(const zc_chess_state& s) {
+    return (s.turn ? chess::MISC_TURN : 0u) | (s.w_ck ? chess::MISC_WCK : 0u) | (s.w_cq ? chess::MISC_WCQ : 0u) |
+           (s.b_ck ? chess::MISC_BCK : 0u) | (s.b_cq ? chess::MISC_BCQ : 0u);
+}
+
+extern "C" int zc_chess_init_state(zc_chess_state* out) {
+    if (!out) return fail(ZC_EINVAL, "out is NULL");
+    memset(out, 0, sizeof *out);
+    memcpy(out->board, "rnbqkbnrpppppppp                                PPPPPPPPRNBQKBNR", 64);
+    out->w_ck = out->w_cq = out->b_ck = out->b_cq = 1;
+    return ZC_OK;
+}
+
+extern "C" int zc_chess_from_fen(const char* fen, zc_chess_state* out) {
+    if (!fen || !out) return fail(ZC_EINVAL, "NULL argument");
+    memset(out, 0, sizeof *out);
+    memset(out->board, ' ', 64);
+    // six whitespace-separated fields; en passant and the full-move number are ignored, a
+    // missing half-move clock reads as 0 (chess_backend.cpp:525-556)
+    std::string f[6];
+    int nf = 0;
+    for (const char* p = fen; *p && nf < 6;) {
+        while (*p == ' ' || *p == '\t' || *p == '\n') ++p;
+        if (!*p) break;
+        const char* q = p;
+        while (*q && *q != ' ' && *q != '\t' && *q != '\n') ++q;
+        f[nf++] = std::string(p, q);
+        p = q;
+    }
+    int idx = 0;
+    for (char ch : f[0]) {
+        if (ch == '/') continue;
+        if (ch >= '0' && ch <= '9') {
+            idx += ch - '0';
+        } else if (idx < 64) {
+            out->board[idx++] = (uint8_t)ch;
+        }
+        if (idx > 64) return fail(ZC_EINVAL, "FEN: more than 64 squares");
+    }
+    out->turn = f[1] == "w" ? 0 : 1;
+    out->w_ck = f[2].find('K') != std::string::npos;
+    out->w_cq = f[2].find('Q') != std::string::npos;
+    out->b_ck = f[2].find('k') != std::string::npos;
+    out->b_cq = f[2].find('q') != std::string::npos;
+    int hm = 0;
+    if (nf >= 5) {
+        char* end = nullptr;
+        const long v = strtol(f[4].c_str(), &end, 10);
+        if (end != f[4].c_str()) hm = (int)v;
+    }
+    out->fifty_move_rule_counter = (uint8_t)hm;
+    return ZC_OK;
+}
+
+extern "C" int zc_chess_legal_moves(const zc_chess_state* s, zc_chess_move* out) {
+    if (!s || !out) return fail(ZC_EINVAL, "NULL argument");
+    const chess::Board b = board_of(*s);
+    uint16_t mv[ChessGame::MOVE_SCRATCH];
+    const int n = chess::generate(b, s->turn ? 1 : 0, mv);
+    for (int i = 0; i < n; ++i) out[i] = decode_move(b, mv[i]);
+    return n;
+}
+
+extern "C" int zc_chess_play_move(const zc_chess_state* s, const zc_chess_move* m, zc_chess_state* out) {
+    if (!s || !m || !out) return fail(ZC_EINVAL, "NULL argument");
+    if (m->fr > 7 || m->fc > 7 || m->tr > 7 || m->tc > 7) return fail(ZC_EINVAL, "move off the board");
+    const chess::Board b = board_of(*s);
+    const int from = m->fr * 8 + m->fc, to = m->tr * 8 + m->tc;
+    uint32_t nm;
+    const chess::Board nb = chess::play(b, misc_of(*s), from, to, nm);
+    zc_chess_state o;
+    memset(&o, 0, sizeof o);
+    for (int i = 0; i < 64; ++i) o.board[i] = chess::char_of_code(chess::piece_at(nb, i));
+    o.turn = (uint8_t)(nm & chess::MISC_TURN);
+    o.w_ck = (nm & chess::MISC_WCK) != 0;
+    o.w_cq = (nm & chess::MISC_WCQ) != 0;
+    o.b_ck = (nm & chess::MISC_BCK) != 0;
+    o.b_cq = (nm & chess::MISC_BCQ) != 0;
+    o.fifty_move_rule_counter = chess::resets_fifty(b, from, to) ? 0 : (uint8_t)(s->fifty_move_rule_counter + 1);
+    *out = o;
+    return ZC_OK;
+}
+
+extern "C" int zc_chess_check_win(const zc_chess_state* s) {
+    if (!s) return fail(ZC_EINVAL, "NULL argument");
+    const chess::Board b = board_of(*s);
+    const int turn = s->turn ? 1 : 0;
+    return chess::generate(b, turn, nullptr) == 0 && chess::in_check(b, turn) ? 1 : 0;
+}
+
+// chess_backend.cpp:148-180: some prefix of the (most-recent-first) list is >= 3 repeats of a period >= 2
+static bool repeated_prefix(const zc_chess_move* L, int n, int min_len, int min_rep) {
+    if (n < min_len * min_rep) return false;
+    auto eq = [&](int a, int b) {
+        return L[a].fr == L[b].fr && L[a].fc == L[b].fc && L[a].tr == L[b].tr && L[a].tc == L[b].tc && L[a].value == L[b].value;
+    };
+    std::vector<int> pi((size_t)n, 0);
+    for (int i = 1, j = 0; i < n; ++i) {
+        while (j > 0 && !eq(i, j)) j = pi[(size_t)j - 1];
+        if (eq(i, j)) ++j;
+        pi[(size_t)i] = j;
+    }
+    for (int i = 0; i < n; ++i) {
+        const int len = i + 1, period = len - pi[(size_t)i];
+        if (period >= min_len && len % period == 0 && len / period >= min_rep) return true;
+    }
+    return false;
+}
+
+extern "C" int zc_chess_check_draw(const zc_chess_state* s, const zc_chess_move* hist_white, int n_white,
+                                   const zc_chess_move* hist_black, int n_black) {
+    if (!s || n_white < 0 || n_black < 0 || (n_white && !hist_white) || (n_black && !hist_black))
+        return fail(ZC_EINVAL, "bad argument");
+    const chess::Board b = board_of(*s);
+    const int turn = s->turn ? 1 : 0;
+    if (chess::generate(b, turn, nullptr) == 0 && !chess::in_check(b, turn)) return 1;   // stalemate branch (:419-427)
+    if (s->fifty_move_rule_counter >= 50) return 1;                                       // plies, :429
+    if (repeated_prefix(hist_white, n_white, 2, 3) && repeated_prefix(hist_black, n_black, 2, 3)) return 1;
+    return 0;
+}
+
+extern "C" int zc_chess_to_tensor(const zc_chess_state* s, float* out) {
+    if (!s || !out) return fail(ZC_EINVAL, "NULL argument");
+    const chess::Board b = board_of(*s);
+    const uint32_t misc = misc_of(*s);
+    for (int pl = 0; pl < 17; ++pl) {
+        const uint64_t bb = ChessGame::plane_bits(b, misc, pl);
+        for (int i = 0; i < 64; ++i) out[pl * 64 + i] = (float)((bb >> i) & 1ull);
+    }
+    return ZC_OK;
+}
+
+// ------------------------------------------------------------------------------------------ device batches
+struct PerftState {
+    chess::Board b;
+    uint32_t misc;
+    uint32_t pad;
+};
+
+__global__ void k_chess_legal_batch(const zc_chess_state* __restrict__ states, int n, zc_chess_move* __restrict__ moves,
+                                    int32_t* __restrict__ counts, int32_t* __restrict__ flags, uint16_t* __restrict__ scratch) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const zc_chess_state s = states[t];
+    const chess::Board b = board_of(s);
+    const int turn = s.turn ? 1 : 0;
+    uint16_t* mv = scratch + (size_t)t * ChessGame::MOVE_SCRATCH;
+    const int k = chess::generate(b, turn, mv);
+    for (int i = 0; i < k; ++i) moves[(size_t)t * ZC_MAX_MOVES + i] = decode_move(b, mv[i]);
+    counts[t] = k;
+    const bool chk = chess::in_check(b, turn);
+    flags[t] = (k == 0 && chk ? 1 : 0) | (k == 0 && !chk ? 2 : 0) | (chk ? 4 : 0);
+}
+
+__global__ void k_perft_count(const PerftState* __restrict__ frontier, unsigned long long n,
+                              unsigned long long* __restrict__ total) {
+    const unsigned long long t = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long mine = 0;
+    if (t < n) mine = (unsigned long long)chess::generate(frontier[t].b, (int)(frontier[t].misc & 1u), nullptr);
+    for (int d = 16; d >= 1; d >>= 1) mine += __shfl_xor_sync(0xFFFFFFFFu, mine, d);
+    if ((threadIdx.x & 31) == 0 && mine) atomicAdd(total, mine);
+}
+
+__global__ void k_perft_expand(const PerftState* __restrict__ frontier, unsigned long long n, PerftState* __restrict__ next,
+                               unsigned long long* __restrict__ cursor, uint16_t* __restrict__ scratch) {
+    const unsigned long long t = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const PerftState s = frontier[t];
+    uint16_t* mv = scratch + t * ChessGame::MOVE_SCRATCH;
+    const int k = chess::generate(s.b, (int)(s.misc & 1u), mv);
+    if (k == 0) return;
+    const unsigned long long base = atomicAdd(cursor, (unsigned long long)k);
+    for (int i = 0; i < k; ++i) {
+        PerftState c;
+        c.b = chess::play(s.b, s.misc, chess::move_from(mv[i]), chess::move_to(mv[i]), c.misc);
+        c.pad = 0;
+        next[base + i] = c;
+    }
+}
+
+static int use_device(int device) {
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(ZC_ENODEVICE, "no CUDA device: libzc_b200 has no CPU path");
+    }
+    if (device < 0 || device >= ndev) return fail(ZC_EINVAL, "device out of range");
+    CUDA_TRY(cudaSetDevice(device));
+    return ZC_OK;
+}
+
+struct DevBuf {   // frees on scope exit
+    void* p = nullptr;
+    ~DevBuf() { cudaFree(p); }
+};
+
+extern "C" int zc_chess_legal_moves_batch(int device, const zc_chess_state* states, int n, zc_chess_move* moves,
+                                          int32_t* counts, int32_t* flags) {
+    if (!states || !moves || !counts || !flags || n < 1) return fail(ZC_EINVAL, "bad argument");
+    if (int rc = use_device(device)) return rc;
+    DevBuf ds, dm, dc, df, dscr;
+    CUDA_TRY(cudaMalloc(&ds.p, sizeof(zc_chess_state) * (size_t)n));
+    CUDA_TRY(cudaMalloc(&dm.p, sizeof(zc_chess_move) * (size_t)n * ZC_MAX_MOVES));
+    CUDA_TRY(cudaMalloc(&dc.p, sizeof(int32_t) * (size_t)n));
+    CUDA_TRY(cudaMalloc(&df.p, sizeof(int32_t) * (size_t)n));
+    CUDA_TRY(cudaMalloc(&dscr.p, sizeof(uint16_t) * (size_t)n * ChessGame::MOVE_SCRATCH));
+    CUDA_TRY(cudaMemcpy(ds.p, states, sizeof(zc_chess_state) * (size_t)n, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemset(dm.p, 0, sizeof(zc_chess_move) * (size_t)n * ZC_MAX_MOVES));
+    k_chess_legal_batch<<<(n + 63) / 64, 64>>>((const zc_chess_state*)ds.p, n, (zc_chess_move*)dm.p, (int32_t*)dc.p,
+                                               (int32_t*)df.p, (uint16_t*)dscr.p);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpy(moves, dm.p, sizeof(zc_chess_move) * (size_t)n * ZC_MAX_MOVES, cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(counts, dc.p, sizeof(int32_t) * (size_t)n, cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(flags, df.p, sizeof(int32_t) * (size_t)n, cudaMemcpyDeviceToHost));
+    return ZC_OK;
+}
+
+extern "C" int zc_chess_perft(int device, const zc_chess_state* root, int depth, uint64_t* out) {
+    if (!root || !out || depth < 1 || depth > 12) return fail(ZC_EINVAL, "bad argument");
+    if (int rc = use_device(device)) return rc;
+    PerftState r0;
+    r0.b = board_of(*root);
+    r0.misc = misc_of(*root);
+    r0.pad = 0;
+    DevBuf cur, counter;
+    unsigned long long n = 1;
+    CUDA_TRY(cudaMalloc(&cur.p, sizeof(PerftState)));
+    CUDA_TRY(cudaMemcpy(cur.p, &r0, sizeof r0, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMalloc(&counter.p, sizeof(unsigned long long)));
+    for (int d = 1; d <= depth; ++d) {
+        // how many positions does the next ply hold?
+        unsigned long long total = 0;
+        CUDA_TRY(cudaMemset(counter.p, 0, sizeof(unsigned long long)));
+        if (n) {
+            k_perft_count<<<(unsigned)((n + 127) / 128), 128>>>((const PerftState*)cur.p, n, (unsigned long long*)counter.p);
+            CUDA_TRY(cudaGetLastError());
+        }
+        CUDA_TRY(cudaMemcpy(&total, counter.p, sizeof total, cudaMemcpyDeviceToHost));
+        if (d == depth) {
+            *out = total;
+            return ZC_OK;
+        }
+        if (total > (1ull << 28)) return fail(ZC_ECAPACITY, "perft frontier too large for one device buffer");
+        DevBuf next, scr;
+        CUDA_TRY(cudaMalloc(&next.p, sizeof(PerftState) * (size_t)(total ? total : 1)));
+        CUDA_TRY(cudaMalloc(&scr.p, sizeof(uint16_t) * (size_t)(n ? n : 1) * ChessGame::MOVE_SCRATCH));
+        CUDA_TRY(cudaMemset(counter.p, 0, sizeof(unsigned long long)));
+        if (n) {
+            k_perft_expand<<<(unsigned)((n + 127) / 128), 128>>>((const PerftState*)cur.p, n, (PerftState*)next.p,
+                                                                 (unsigned long long*)counter.p, (uint16_t*)scr.p);
+            CUDA_TRY(cudaGetLastError());
+        }
+        CUDA_TRY(cudaDeviceSynchronize());
+        std::swap(cur.p, next.p);
+        n = total;
+    }
+    return ZC_OK;
+}
+
+__global__ void k_c4_rules_batch(const zc_c4_state* __restrict__ states, int n, uint8_t* __restrict__ cols,
+                                 int32_t* __restrict__ flags) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const zc_c4_state s = states[t];
+    c4::State r;
+    r.cur = s.turn == 0 ? s.x : s.o;
+    r.opp = s.turn == 0 ? s.o : s.x;
+    const int mask = c4::legal_mask(r), k = zc_popc32((unsigned)mask);
+    for (int i = 0; i < 8; ++i) cols[(size_t)t * 8 + i] = i < k ? (uint8_t)c4::move_col(mask, i) : 255;
+    flags[t] = (c4::check_win(r) ? 1 : 0) | (c4::check_draw(r) ? 2 : 0);
+}
+
+extern "C" int zc_c4_rules_batch(int device, const zc_c4_state* states, int n, uint8_t* cols, int32_t* flags) {
+    if (!states || !cols || !flags || n < 1) return fail(ZC_EINVAL, "bad argument");
+    if (int rc = use_device(device)) return rc;
+    if (int rc = upload_order()) return rc;
+    DevBuf ds, dc, df;
+    CUDA_TRY(cudaMalloc(&ds.p, sizeof(zc_c4_state) * (size_t)n));
+    CUDA_TRY(cudaMalloc(&dc.p, (size_t)n * 8));
+    CUDA_TRY(cudaMalloc(&df.p, sizeof(int32_t) * (size_t)n));
+    CUDA_TRY(cudaMemcpy(ds.p, states, sizeof(zc_c4_state) * (size_t)n, cudaMemcpyHostToDevice));
+    k_c4_rules_batch<<<(n + 127) / 128, 128>>>((const zc_c4_state*)ds.p, n, (uint8_t*)dc.p, (int32_t*)df.p);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpy(cols, dc.p, (size_t)n * 8, cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(flags, df.p, sizeof(int32_t) * (size_t)n, cudaMemcpyDeviceToHost));
+    return ZC_OK;
+}

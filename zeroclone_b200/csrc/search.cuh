@@ -42,6 +42,7 @@ struct SearchParams {
     double c;
     uint64_t seed;
     // split-phase leaf packing
+    uint16_t* scratch;       // chess: [warp slot][32 lanes][MOVE_SCRATCH] packed moves
     void* planes;
     int plane_dtype;
     const float* values;
@@ -92,8 +93,8 @@ struct Leaf {
 };
 
 template <class G, bool kBuiltinEval>
-ZC_D bool select_expand(const SearchParams& p, uint4* __restrict__ arena, uint2* __restrict__ path, TreeCtl& ctl,
-                        int B, int lane, int& D_out, Leaf<G>& leaf) {
+ZC_D bool select_expand(const SearchParams& p, typename G::Ctx& gx, uint4* __restrict__ arena, uint2* __restrict__ path,
+                        TreeCtl& ctl, int B, int lane, int& D_out, Leaf<G>& leaf) {
     // ---- frozen descent (mcts.cpp:47-63)
     uint32_t node = 0;
     int depth = 0;
@@ -173,7 +174,7 @@ ZC_D bool select_expand(const SearchParams& p, uint4* __restrict__ arena, uint2*
         if (act) {
             ei = expansion_order(p.policy, Pk, Pnexp + j);
             cs = G::child(Pst, Pmisc, arena + P, Pk, ei, cmisc);
-            ck = G::count_moves(cs, cmisc);
+            ck = G::count_moves(gx, cs, cmisc);
         }
         const int csize = act ? 1 + G::SS + ck + G::move_slots(ck) : 0;
         int total;
@@ -187,7 +188,7 @@ ZC_D bool select_expand(const SearchParams& p, uint4* __restrict__ arena, uint2*
             my_slot = base + (uint32_t)off;
             arena[my_slot] = make_hdr(0, (uint32_t)ck, 0, P, (uint32_t)ei, cmisc, (uint32_t)(D + 1));
             G::store_state(arena + my_slot + 1, cs);
-            G::store_moves(arena + my_slot + 1 + G::SS + ck, cs, cmisc, ck);
+            G::store_moves(gx, arena + my_slot + 1 + G::SS + ck, ck);
             arena[P + 1 + G::SS + ei].w = my_slot;                     // children[move_idx] = child (:76)
             leaf.info = (uint32_t)D | ((uint32_t)ei << LEAF_EDGE_SHIFT);
             leaf.st = cs;
@@ -196,6 +197,7 @@ ZC_D bool select_expand(const SearchParams& p, uint4* __restrict__ arena, uint2*
         }
         Pnexp += m;
         if (lane == 0) arena[P].y = (uint32_t)Pk | ((uint32_t)Pnexp << 16);   // untried.erase (:72)
+        __syncwarp();   // the new nodes (incl. their move lists) are visible to the whole warp
         ctl.top += (uint32_t)total;
         ctl.nodes += (uint32_t)m;
         ctl.sum_leaf_depth += (unsigned long long)m * (unsigned)(D + 1);
@@ -307,11 +309,12 @@ __global__ void __launch_bounds__(SEARCH_BLOCK) k_search_fused(SearchParams p) {
         uint4* arena = p.arena + (uint64_t)tree * p.arena_slots;
         uint2* path = p.path + (uint64_t)tree * p.path_cap;
         TreeCtl ctl = p.ctl[tree];
+        typename G::Ctx gx = G::make_ctx(p, (blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5, lane);
         for (int done = 0; done < p.simulations && ctl.status == 0;) {
             const int B = min(p.batch_size, p.simulations - done);
             int D;
             Leaf<G> leaf;
-            if (!select_expand<G, true>(p, arena, path, ctl, B, lane, D, leaf)) break;
+            if (!select_expand<G, true>(p, gx, arena, path, ctl, B, lane, D, leaf)) break;
             backprop_batch<G>(arena, path, B, D, lane, leaf.info, leaf.value);
             done += B;
             ctl.sims_done += (uint32_t)B;
@@ -335,7 +338,8 @@ __global__ void __launch_bounds__(SEARCH_BLOCK) k_select(SearchParams p, int sim
     Leaf<G> leaf;
     leaf.info = 0;
     bool ok = B > 0;
-    if (ok) ok = select_expand<G, false>(p, arena, path, ctl, B, lane, D, leaf);
+    typename G::Ctx gx = G::make_ctx(p, (unsigned)tree, lane);
+    if (ok) ok = select_expand<G, false>(p, gx, arena, path, ctl, B, lane, D, leaf);
     if (lane == 0) {
         pd->B = ok ? B : 0;
         pd->D = D;

@@ -2,6 +2,7 @@
 // Host side: handle bookkeeping, launches, copies.  No CPU implementation of the search exists.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -10,6 +11,7 @@
 
 #include "../../include/zc_b200.h"
 #include "c4_game.cuh"
+#include "chess_game.cuh"
 #include "search.cuh"
 
 namespace zc {
@@ -46,6 +48,7 @@ struct zc_search {
     Pending* pending = nullptr;
     double* log_tab = nullptr;
     unsigned int* work_counter = nullptr;
+    uint16_t* scratch = nullptr;        // chess move staging, one buffer per lane
     void* roots_dev = nullptr;          // staging for host roots
     zc_root_result* res_dev = nullptr;
     int32_t* visits_dev = nullptr;
@@ -181,6 +184,96 @@ __global__ void k_results_c4(const uint4* __restrict__ arena_all, uint64_t arena
     res[t] = r;
 }
 
+
+__global__ void k_set_roots_chess(const zc_chess_state* __restrict__ roots, uint4* __restrict__ arena_all,
+                                  uint64_t arena_slots, TreeCtl* __restrict__ ctl, Pending* __restrict__ pending,
+                                  uint16_t* __restrict__ scratch, int n) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const zc_chess_state r = roots[t];
+    chess::Board b = {0, 0, 0, 0};
+    for (int i = 0; i < 64; ++i) chess::put_piece(b, i, chess::code_of_char(r.board[i]));
+    const uint32_t misc = (r.turn ? chess::MISC_TURN : 0u) | (r.w_ck ? chess::MISC_WCK : 0u) | (r.w_cq ? chess::MISC_WCQ : 0u) |
+                          (r.b_ck ? chess::MISC_BCK : 0u) | (r.b_cq ? chess::MISC_BCQ : 0u);
+    ChessGame::Ctx gx;
+    gx.moves = scratch + (size_t)t * 32 * ChessGame::MOVE_SCRATCH;
+    const int k = ChessGame::count_moves(gx, b, misc);
+    uint4* arena = arena_all + (uint64_t)t * arena_slots;
+    arena[0] = make_hdr(0, (uint32_t)k, 0, 0, 0, misc, 0);
+    ChessGame::store_state(arena + 1, b);
+    for (int i = 0; i < k; ++i) arena[3 + i] = make_uint4(0, 0, 0, 0);
+    ChessGame::store_moves(gx, arena + 3 + k, k);
+    TreeCtl c;
+    memset(&c, 0, sizeof c);
+    c.top = (uint32_t)(3 + k + ChessGame::move_slots(k));
+    c.nodes = 1;
+    c.root_turn = r.turn;
+    ctl[t] = c;
+    pending[t].B = 0;
+}
+
+__device__ __host__ inline zc_chess_move decode_move(const chess::Board& b, uint16_t m) {
+    zc_chess_move mv;
+    const int f = chess::move_from(m), t = chess::move_to(m);
+    mv.fr = (uint8_t)(f >> 3);
+    mv.fc = (uint8_t)(f & 7);
+    mv.tr = (uint8_t)(t >> 3);
+    mv.tc = (uint8_t)(t & 7);
+    mv.value = (float)chess::capture_value(chess::piece_at(b, t));
+    return mv;
+}
+
+__global__ void k_results_chess(const uint4* __restrict__ arena_all, uint64_t arena_slots, const TreeCtl* __restrict__ ctl,
+                                int n, zc_root_result* __restrict__ res, int32_t* __restrict__ visits,
+                                double* __restrict__ wsum, zc_chess_move* __restrict__ moves, int stride) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const uint4* arena = arena_all + (uint64_t)t * arena_slots;
+    const uint4 hd = arena[0];
+    const int k = (int)hdr_k(hd);
+    const chess::Board b = ChessGame::load_state(arena + 1);
+    int best = -1, best_n = -1;
+    for (int i = 0; i < k; ++i) {
+        const uint4 e = arena[3 + i];
+        if (e.w && (int)e.z > best_n) { best_n = (int)e.z; best = i; }      // mcts.cpp:150-155
+        if (i < stride) {
+            if (visits) visits[(size_t)t * stride + i] = (int)e.z;
+            if (wsum) wsum[(size_t)t * stride + i] = edge_W(e);
+            if (moves) moves[(size_t)t * stride + i] = decode_move(b, ChessGame::move_at(arena, k, i));
+        }
+    }
+    const TreeCtl c = ctl[t];
+    zc_root_result r;
+    memset(&r, 0, sizeof r);
+    r.n_moves = k;
+    r.best = best;
+    r.root_visits = (int)hd.x;
+    r.status = c.status;
+    if (best >= 0) {
+        const zc_chess_move mv = decode_move(b, ChessGame::move_at(arena, k, best));
+        r.best_move[0] = mv.fr; r.best_move[1] = mv.fc; r.best_move[2] = mv.tr; r.best_move[3] = mv.tc;
+        r.best_move_value = mv.value;
+    } else {
+        r.best_move[0] = r.best_move[1] = r.best_move[2] = r.best_move[3] = 255;
+    }
+    r.nodes = (int)c.nodes;
+    r.sum_leaf_depth = (int64_t)c.sum_leaf_depth;
+    r.max_leaf_depth = (int)c.max_leaf_depth;
+    r.reevaluated_leaves = (int)c.reevaluated;
+    res[t] = r;
+}
+
+#define ZC_DISPATCH(game, ...)                 \
+    do {                                       \
+        if ((game) == ZC_GAME_C4) {            \
+            using G = C4Game;                  \
+            __VA_ARGS__;                       \
+        } else {                               \
+            using G = ChessGame;               \
+            __VA_ARGS__;                       \
+        }                                      \
+    } while (0)
+
 // ------------------------------------------------------------------------------- handle
 static int check_handle(const zc_search* h) {
     if (!h) return fail(ZC_EINVAL, "handle is NULL");
@@ -191,7 +284,7 @@ extern "C" int zc_search_create(int game, int device, int max_trees, int max_sim
                                 zc_search** out) {
     if (!out) return fail(ZC_EINVAL, "out is NULL");
     *out = nullptr;
-    if (game != ZC_GAME_C4) return fail(ZC_EINVAL, "unknown game");
+    if (game != ZC_GAME_C4 && game != ZC_GAME_CHESS) return fail(ZC_EINVAL, "unknown game");
     if (max_trees < 1 || max_sims < 1) return fail(ZC_EINVAL, "max_trees and max_sims must be >= 1");
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
@@ -205,7 +298,7 @@ extern "C" int zc_search_create(int game, int device, int max_trees, int max_sim
     h->device = device;
     h->max_trees = max_trees;
     h->max_sims = max_sims;
-    const int per_node = game == ZC_GAME_C4 ? 1 + C4Game::SS + 7 : 48;
+    const int per_node = game == ZC_GAME_C4 ? 1 + C4Game::SS + 7 : 72;
     h->arena_slots = arena_slots_per_tree > 0 ? (uint64_t)arena_slots_per_tree : (uint64_t)(max_sims + 1) * per_node;
     h->arena_slots = (h->arena_slots + 1) & ~1ull;   // keep every tree's arena 32-byte aligned
     h->path_cap = (uint32_t)max_sims + 40u;
@@ -239,9 +332,22 @@ extern "C" int zc_search_create(int game, int device, int max_trees, int max_sim
     }
     CUDA_TRY(cudaMemcpy(h->log_tab, lt.data(), lt.size() * sizeof(double), cudaMemcpyHostToDevice));
     int occ = 0, sms = 0;
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_search_fused<C4Game>, SEARCH_BLOCK, 0));
+    if (game == ZC_GAME_C4)
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_search_fused<C4Game>, SEARCH_BLOCK, 0));
+    else
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_search_fused<ChessGame>, SEARCH_BLOCK, 0));
     CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
     h->fused_grid = occ * sms;
+    if (game == ZC_GAME_CHESS) {
+        const size_t warps = (size_t)std::max(max_trees, h->fused_grid * (SEARCH_BLOCK / 32));
+        const size_t sb = warps * 32 * ChessGame::MOVE_SCRATCH * sizeof(uint16_t);
+        h->bytes += (int64_t)sb;
+        cudaError_t se = cudaMalloc((void**)&h->scratch, sb);
+        if (se != cudaSuccess) {
+            zc_search_destroy(h);
+            return fail(ZC_ECUDA, std::string("cudaMalloc(scratch): ") + cudaGetErrorString(se));
+        }
+    }
     *out = h;
     return ZC_OK;
 }
@@ -255,6 +361,7 @@ extern "C" int zc_search_destroy(zc_search* h) {
     cudaFree(h->pending);
     cudaFree(h->log_tab);
     cudaFree(h->work_counter);
+    cudaFree(h->scratch);
     cudaFree(h->roots_dev);
     cudaFree(h->res_dev);
     cudaFree(h->visits_dev);
@@ -274,8 +381,12 @@ static int set_roots_common(zc_search* h, const void* dev_states, int n, cudaStr
         if (int rc = upload_order()) return rc;
         h->order_version = g_order_version;
     }
-    k_set_roots_c4<<<(n + 127) / 128, 128, 0, st>>>((const zc_c4_state*)dev_states, h->arena, h->arena_slots, h->ctl,
-                                                  h->pending, n);
+    if (h->game == ZC_GAME_C4)
+        k_set_roots_c4<<<(n + 127) / 128, 128, 0, st>>>((const zc_c4_state*)dev_states, h->arena, h->arena_slots, h->ctl,
+                                                      h->pending, n);
+    else
+        k_set_roots_chess<<<(n + 63) / 64, 64, 0, st>>>((const zc_chess_state*)dev_states, h->arena, h->arena_slots, h->ctl,
+                                                      h->pending, h->scratch, n);
     h->launches++;
     CUDA_TRY(cudaGetLastError());
     return ZC_OK;
@@ -318,6 +429,7 @@ static SearchParams make_params(zc_search* h, int sims, double c, int batch, int
     p.policy = policy;
     p.c = c;
     p.seed = seed;
+    p.scratch = h->scratch;
     return p;
 }
 
@@ -333,15 +445,16 @@ extern "C" int zc_search_run(zc_search* h, int simulations, double c, int batch_
                              uint64_t seed, void* stream) {
     if (int rc = check_handle(h)) return rc;
     if (int rc = check_search_args(h, simulations, batch_size, policy)) return rc;
-    if (evaluator != ZC_EVAL_C4_TERMINAL && evaluator != ZC_EVAL_C4_POSITIONAL)
-        return fail(ZC_EINVAL, "evaluator is not a built-in evaluator of this game");
+    const bool ev_ok = h->game == ZC_GAME_C4 ? (evaluator == ZC_EVAL_C4_TERMINAL || evaluator == ZC_EVAL_C4_POSITIONAL)
+                                             : evaluator == ZC_EVAL_CHESS_CRUDE;
+    if (!ev_ok) return fail(ZC_EINVAL, "evaluator is not a built-in evaluator of this game");
     CUDA_TRY(cudaSetDevice(h->device));
     cudaStream_t st = (cudaStream_t)stream;
     SearchParams p = make_params(h, simulations, c, batch_size, evaluator, policy, seed);
     CUDA_TRY(cudaMemsetAsync(h->work_counter, 0, sizeof(unsigned int), st));
     const int blocks_needed = (h->n_trees * 32 + SEARCH_BLOCK - 1) / SEARCH_BLOCK;
     const int grid = blocks_needed < h->fused_grid ? blocks_needed : h->fused_grid;
-    k_search_fused<C4Game><<<grid, SEARCH_BLOCK, 0, st>>>(p);
+    ZC_DISPATCH(h->game, k_search_fused<G><<<grid, SEARCH_BLOCK, 0, st>>>(p));
     h->launches++;
     CUDA_TRY(cudaGetLastError());
     return ZC_OK;
@@ -371,7 +484,7 @@ extern "C" int zc_search_select(zc_search* h, void* dev_planes, int plane_dtype,
     p.planes = dev_planes;
     p.plane_dtype = plane_dtype;
     const int grid = (h->n_trees * 32 + SEARCH_BLOCK - 1) / SEARCH_BLOCK;
-    k_select<C4Game><<<grid, SEARCH_BLOCK, 0, st>>>(p, h->sp_left);
+    ZC_DISPATCH(h->game, k_select<G><<<grid, SEARCH_BLOCK, 0, st>>>(p, h->sp_left));
     h->launches++;
     CUDA_TRY(cudaGetLastError());
     h->sp_selected = h->sp_left < h->sp_batch ? h->sp_left : h->sp_batch;
@@ -387,7 +500,7 @@ extern "C" int zc_search_backprop(zc_search* h, const float* dev_values, void* s
     SearchParams p = make_params(h, h->sp_left, h->sp_c, h->sp_batch, ZC_EVAL_EXTERNAL, h->sp_policy, h->sp_seed);
     p.values = dev_values;
     const int grid = (h->n_trees * 32 + SEARCH_BLOCK - 1) / SEARCH_BLOCK;
-    k_backprop<C4Game><<<grid, SEARCH_BLOCK, 0, st>>>(p);
+    ZC_DISPATCH(h->game, k_backprop<G><<<grid, SEARCH_BLOCK, 0, st>>>(p));
     h->launches++;
     CUDA_TRY(cudaGetLastError());
     h->sp_left -= h->sp_selected;
@@ -419,9 +532,14 @@ extern "C" int zc_search_results(zc_search* h, zc_root_result* results, int32_t*
         CUDA_TRY(cudaMemsetAsync(h->wsum_dev, 0, sizeof(double) * (size_t)n * stride, st));
         CUDA_TRY(cudaMemsetAsync(h->moves_dev, 0, sizeof(zc_chess_move) * (size_t)n * stride, st));
     }
-    k_results_c4<<<(n + 127) / 128, 128, 0, st>>>(h->arena, h->arena_slots, h->ctl, n, h->res_dev,
-                                                visits ? h->visits_dev : nullptr, value_sums ? h->wsum_dev : nullptr,
-                                                moves ? h->moves_dev : nullptr, stride);
+    if (h->game == ZC_GAME_C4)
+        k_results_c4<<<(n + 127) / 128, 128, 0, st>>>(h->arena, h->arena_slots, h->ctl, n, h->res_dev,
+                                                    visits ? h->visits_dev : nullptr, value_sums ? h->wsum_dev : nullptr,
+                                                    moves ? h->moves_dev : nullptr, stride);
+    else
+        k_results_chess<<<(n + 127) / 128, 128, 0, st>>>(h->arena, h->arena_slots, h->ctl, n, h->res_dev,
+                                                       visits ? h->visits_dev : nullptr, value_sums ? h->wsum_dev : nullptr,
+                                                       moves ? h->moves_dev : nullptr, stride);
     h->launches++;
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaMemcpyAsync(results, h->res_dev, sizeof(zc_root_result) * n, cudaMemcpyDeviceToHost, st));
@@ -439,7 +557,7 @@ extern "C" int zc_search_tree_hash(zc_search* h, uint64_t* host_hashes, void* st
     if (!host_hashes || h->n_trees < 1) return fail(ZC_EINVAL, "tree_hash: bad arguments");
     CUDA_TRY(cudaSetDevice(h->device));
     cudaStream_t st = (cudaStream_t)stream;
-    k_tree_hash<C4Game><<<(h->n_trees + 63) / 64, 64, 0, st>>>(h->arena, h->arena_slots, h->n_trees, h->hash_dev);
+    ZC_DISPATCH(h->game, k_tree_hash<G><<<(h->n_trees + 63) / 64, 64, 0, st>>>(h->arena, h->arena_slots, h->n_trees, h->hash_dev));
     h->launches++;
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaMemcpyAsync(host_hashes, h->hash_dev, sizeof(uint64_t) * h->n_trees, cudaMemcpyDeviceToHost, st));
@@ -467,3 +585,5 @@ extern "C" int zc_search_get_counters(zc_search* h, zc_search_counters* out, voi
     }
     return ZC_OK;
 }
+
+#include "rules_api.inl"

@@ -32,3 +32,11 @@ ZC_HD int zc_ctz64(uint64_t v) {
     return __builtin_ctzll(v);
 #endif
 }
+// number of leading zero bits (v != 0)
+ZC_HD int zc_clz64(uint64_t v) {
+#ifdef __CUDA_ARCH__
+    return __clzll((long long)v);
+#else
+    return __builtin_clzll(v);
+#endif
+}
