@@ -1,0 +1,3 @@
+from engine._alias import alias
+
+alias(__name__, "zeroclone_b200.models.chess_value.network")

@@ -46,10 +46,12 @@ struct C4Game {
         return c4::play(parent, c4::move_col(c4::legal_mask(parent), ei));
     }
     ZC_HD static int count_moves(Ctx&, const State& s, uint32_t) { return c4::n_moves(s); }
-    ZC_HD static double eval(const State& s, uint32_t, int evaluator) {
-        return evaluator == ZC_EVAL_C4_POSITIONAL ? c4::eval_positional(s) : c4::eval_terminal(s);
+    ZC_HD static double eval(const State& s, uint32_t, int evaluator, uint64_t key) {
+        if (evaluator == ZC_EVAL_C4_POSITIONAL) return c4::eval_positional(s);
+        if (evaluator == ZC_EVAL_C4_ROLLOUT) return c4::eval_rollout(s, key);
+        return c4::eval_terminal(s);
     }
-    ZC_HD static double eval_child(const State& s, uint32_t m, int, int evaluator) { return eval(s, m, evaluator); }
+    ZC_HD static double eval_child(const State& s, uint32_t m, int, int evaluator, uint64_t key) { return eval(s, m, evaluator, key); }
 
     // leaf -> network input row: plane 0 = side to move, plane 1 = opponent, [r][c] with r = 0 the top row
     ZC_D static void pack_planes(void* planes, int dtype, size_t row, bool valid, bool in_range, const State& s, uint32_t) {

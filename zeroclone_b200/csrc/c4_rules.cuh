@@ -91,5 +91,30 @@ ZC_HD double eval_positional(const State& s) {
     return (double)acc * (1.0 / 64.0);
 }
 
+// ZC_EVAL_C4_ROLLOUT: random_rollout (value_functions.py:35-45): uniformly random legal moves until
+// check_win or check_draw; -1 if the side to move at `s` ends up the loser, +1 if the winner, 0 on a
+// draw; an already-won state returns -1 at once.  Device RNG: statistically, not bitwise, the
+// reference (which draws from CPython's global Mersenne Twister).
+ZC_HD uint64_t c4_rng_next(uint64_t& z) {
+    z += 0x9E3779B97F4A7C15ull;
+    uint64_t x = z;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+}
+ZC_HD double eval_rollout(const State& s0, uint64_t key) {
+    State s = s0;
+    int flips = 0;   // parity of plies played: the loser is the side to move when a win is found
+    for (;;) {
+        if (check_win(s)) return (flips & 1) ? 1.0 : -1.0;
+        if (check_draw(s)) return 0.0;
+        const int mask = legal_mask(s), n = zc_popc32((unsigned)mask);
+        if (n == 0) return 0.0;   // unreachable for boards without gaps (a full top row is a full board)
+        const int pick = (int)((c4_rng_next(key) >> 33) % (uint64_t)n);
+        s = play(s, move_col(mask, pick));
+        ++flips;
+    }
+}
+
 }  // namespace c4
 }  // namespace zc

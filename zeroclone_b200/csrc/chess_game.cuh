@@ -68,8 +68,8 @@ struct ChessGame {
         const uint4* src = reinterpret_cast<const uint4*>(gx.moves);
         for (int i = 0; i < move_slots(k); ++i) dst[i] = src[i];
     }
-    ZC_HD static double eval(const State& s, uint32_t misc, int) { return chess::crude_score(s, (int)(misc & 1u), 0); }
-    ZC_HD static double eval_child(const State& s, uint32_t misc, int k, int) { return chess::crude_score(s, (int)(misc & 1u), k); }
+    ZC_HD static double eval(const State& s, uint32_t misc, int, uint64_t) { return chess::crude_score(s, (int)(misc & 1u), 0); }
+    ZC_HD static double eval_child(const State& s, uint32_t misc, int k, int, uint64_t) { return chess::crude_score(s, (int)(misc & 1u), k); }
 
     // chess_backend.cpp:461-521 -- 17 planes x 64 cells; planes 0-11 'PNBRQKpnbrqk', 12 white to move,
     // 13-16 castling flags.  Cell order r*8+c = bit order of the boards.

@@ -67,9 +67,43 @@ ZC_D int warp_excl_scan(int v, int lane, int& total) {
     return x - v;
 }
 
-// j-th move to be expanded at a node with k moves (mcts.cpp:65-78 with policy = first / last
-// element of the untried list; both keep `untried` an interval, so the order is a function of j)
-ZC_D int expansion_order(int policy, int k, int j) { return policy == 1 /*ZC_POLICY_LAST*/ ? k - 1 - j : j; }
+// ---- counter-based RNG (splitmix64 finaliser): every random draw is a pure function of a key
+ZC_HD uint64_t rng_mix(uint64_t z) {
+    z += 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+
+// Keyed pseudo-random bijection of [0,k): three multiply/xorshift/add rounds on b = ceil(log2 k)
+// bits (each round is invertible mod 2^b), cycle-walked into range.  Used for Policy.random
+// (policy_functions.py:10-12): expanding moves in the order perm(0), perm(1), ... draws each next
+// move uniformly from the untried ones, which is what random.choice on the untried list does.
+ZC_HD int keyed_perm(int k, int j, uint64_t key) {
+    if (k <= 1) return 0;
+    int b = 1;
+    while ((1 << b) < k) ++b;
+    const uint32_t mask = (1u << b) - 1u;
+    const uint32_t m1 = ((uint32_t)key | 1u), m2 = ((uint32_t)(key >> 20) | 1u), m3 = ((uint32_t)(key >> 40) | 1u);
+    const uint32_t a1 = (uint32_t)(key >> 8), a2 = (uint32_t)(key >> 29), sh = (uint32_t)((b + 1) >> 1);
+    uint32_t x = (uint32_t)j;
+    do {
+        x = (x * m1 + a1) & mask;
+        x ^= x >> sh;
+        x = (x * m2 + a2) & mask;
+        x ^= x >> sh;
+        x = (x * m3) & mask;
+    } while (x >= (uint32_t)k);
+    return (int)x;
+}
+
+// j-th move to be expanded at a node with k moves (mcts.cpp:65-78).  first / last element of the
+// untried list keep `untried` an interval; random is a keyed permutation; all are functions of j.
+ZC_D int expansion_order(int policy, int k, int j, uint64_t node_key) {
+    if (policy == 0) return j;               // ZC_POLICY_FIRST
+    if (policy == 1) return k - 1 - j;       // ZC_POLICY_LAST
+    return keyed_perm(k, j, node_key);       // ZC_POLICY_RANDOM
+}
 
 // UCB1, mcts.cpp:41-45, with the operation sequence of the reference build
 // (log; divide; sqrt; FUSED multiply-add -- see oracle/zc_oracle.c:uct).
@@ -157,7 +191,8 @@ ZC_D bool select_expand(const SearchParams& p, typename G::Ctx& gx, uint4* __res
                 leaf.info = LEAF_SELF | (uint32_t)D;
                 leaf.st = Pst;
                 leaf.misc = Pmisc;
-                if (kBuiltinEval) leaf.value = G::eval(Pst, Pmisc, p.evaluator);
+                if (kBuiltinEval)
+                    leaf.value = G::eval(Pst, Pmisc, p.evaluator, rng_mix(p.seed ^ ((uint64_t)ctl.tree_id << 32) ^ ((uint64_t)ctl.sims_done << 8) ^ (uint64_t)lane));
             }
             ctl.reevaluated += (uint32_t)(B - made);
             ctl.sum_leaf_depth += (unsigned long long)(B - made) * (unsigned)D;
@@ -172,7 +207,7 @@ ZC_D bool select_expand(const SearchParams& p, typename G::Ctx& gx, uint4* __res
         typename G::State cs = Pst;
         uint32_t cmisc = 0;
         if (act) {
-            ei = expansion_order(p.policy, Pk, Pnexp + j);
+            ei = expansion_order(p.policy, Pk, Pnexp + j, rng_mix(p.seed ^ ((uint64_t)ctl.tree_id << 32) ^ (uint64_t)P));
             cs = G::child(Pst, Pmisc, arena + P, Pk, ei, cmisc);
             ck = G::count_moves(gx, cs, cmisc);
         }
@@ -193,7 +228,8 @@ ZC_D bool select_expand(const SearchParams& p, typename G::Ctx& gx, uint4* __res
             leaf.info = (uint32_t)D | ((uint32_t)ei << LEAF_EDGE_SHIFT);
             leaf.st = cs;
             leaf.misc = cmisc;
-            if (kBuiltinEval) leaf.value = G::eval_child(cs, cmisc, ck, p.evaluator);
+            if (kBuiltinEval)
+                leaf.value = G::eval_child(cs, cmisc, ck, p.evaluator, rng_mix(p.seed ^ ((uint64_t)ctl.tree_id << 32) ^ ((uint64_t)my_slot << 1) ^ 1ull));
         }
         Pnexp += m;
         if (lane == 0) arena[P].y = (uint32_t)Pk | ((uint32_t)Pnexp << 16);   // untried.erase (:72)

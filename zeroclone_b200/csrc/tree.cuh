@@ -32,7 +32,7 @@ struct __align__(16) TreeCtl {
     uint32_t reevaluated;
     unsigned long long sum_path_children;
     uint32_t root_turn;  // C4: whose discs `cur` are at the root (for readout)
-    uint32_t pad;
+    uint32_t tree_id;    // RNG stream id (set at set_roots)
 };
 
 // split-phase (external evaluator) hand-over between select and backprop

@@ -139,6 +139,7 @@ __global__ void k_set_roots_c4(const zc_c4_state* __restrict__ roots, uint4* __r
     c.top = (uint32_t)(2 + k);
     c.nodes = 1;
     c.root_turn = (uint32_t)r.turn;
+    c.tree_id = (uint32_t)t;
     ctl[t] = c;
     pending[t].B = 0;
 }
@@ -208,6 +209,7 @@ __global__ void k_set_roots_chess(const zc_chess_state* __restrict__ roots, uint
     c.top = (uint32_t)(3 + k + ChessGame::move_slots(k));
     c.nodes = 1;
     c.root_turn = r.turn;
+    c.tree_id = (uint32_t)t;
     ctl[t] = c;
     pending[t].B = 0;
 }
@@ -437,7 +439,8 @@ static int check_search_args(zc_search* h, int sims, int batch, int policy) {
     if (h->n_trees < 1) return fail(ZC_ESTATE, "no roots set");
     if (sims < 0 || sims > h->max_sims) return fail(ZC_EINVAL, "simulations exceeds max_sims of the handle");
     if (batch < 1 || batch > 32) return fail(ZC_EINVAL, "batch_size must be in 1..32");
-    if (policy != ZC_POLICY_FIRST && policy != ZC_POLICY_LAST) return fail(ZC_EINVAL, "unsupported policy");
+    if (policy != ZC_POLICY_FIRST && policy != ZC_POLICY_LAST && policy != ZC_POLICY_RANDOM)
+        return fail(ZC_EINVAL, "unsupported policy");
     return ZC_OK;
 }
 
@@ -445,7 +448,7 @@ extern "C" int zc_search_run(zc_search* h, int simulations, double c, int batch_
                              uint64_t seed, void* stream) {
     if (int rc = check_handle(h)) return rc;
     if (int rc = check_search_args(h, simulations, batch_size, policy)) return rc;
-    const bool ev_ok = h->game == ZC_GAME_C4 ? (evaluator == ZC_EVAL_C4_TERMINAL || evaluator == ZC_EVAL_C4_POSITIONAL)
+    const bool ev_ok = h->game == ZC_GAME_C4 ? (evaluator == ZC_EVAL_C4_TERMINAL || evaluator == ZC_EVAL_C4_POSITIONAL || evaluator == ZC_EVAL_C4_ROLLOUT)
                                              : evaluator == ZC_EVAL_CHESS_CRUDE;
     if (!ev_ok) return fail(ZC_EINVAL, "evaluator is not a built-in evaluator of this game");
     CUDA_TRY(cudaSetDevice(h->device));
