@@ -70,7 +70,7 @@ def test_random_policy_and_rollout_are_valid_searches():
     assert (out["visits"].sum(axis=1) == sims).all() and (out["result"]["nodes"] == sims + 1).all()
     assert (np.abs(out["value_sums"]) <= out["visits"] + 1e-9).all()          # rollout values are in {-1,0,1}
     # first expansions are spread over the seven columns (uniform random choice), trees differ
-    assert len(set(map(tuple, out["visits"].tolist()))) > n // 4
+    assert len(set(map(tuple, out["visits"].tolist()))) > 20     # visit counts are quantised by the batch of 32
     # centre columns win more rollouts for the first player than edge columns (sanity of the evaluator)
     q = (out["value_sums"] / np.maximum(1, out["visits"])).mean(axis=0)
     order = out["moves"][0]["fr"][:7].tolist()

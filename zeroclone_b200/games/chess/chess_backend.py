@@ -36,9 +36,9 @@ class State:
         return f"<chess State turn={self.turn} fifty={self.fifty_move_rule_counter} board={bytes(self.board).decode()!r}>"
 
 
-def pack_state(state) -> tuple:
-    return (bytes(state.board), state.turn, state.fifty_move_rule_counter & 0xFF, int(state.w_ck), int(state.w_cq),
-            int(state.b_ck), int(state.b_cq))
+def pack_state(state):
+    """State -> one zc_chess_state record (numpy void of STATE_DTYPE)"""
+    return np.frombuffer(bytes(_c(state)), dtype=STATE_DTYPE)[0]
 
 
 def _c(state) -> _ffi.ChessState:
