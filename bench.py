@@ -37,6 +37,11 @@ WORKLOADS = {
                               "value tower 128ch x 8 blocks on 2x6x7 planes"),
     "c4_heuristic": dict(game="connect4", evaluator="c4_positional", trees=32768, sims=800,
                          desc="Connect Four, deterministic evaluator (parity configuration), 32768 trees x 800 sims"),
+    "chess_crude": dict(game="chess", evaluator="chess_crude", trees=16384, sims=1600,
+                        desc="BASELINE configs[4]: chess configs/crude_chess.yaml heuristic evaluator, 16384 trees x 1600 sims per GPU"),
+    "chess_value_net": dict(game="chess", evaluator="value_net", trees=2048, sims=800,
+                            desc="BASELINE configs[3]: chess configs/chess_value.yaml, movegen kernel + value-net leaf batching, "
+                                 "2048 trees x 800 sims"),
 }
 C_UCT, BATCH = 1.4, 32
 
@@ -85,6 +90,13 @@ class ClockSampler:
             for nme, v in zip(names, r[3:7]):
                 if v.lower().startswith("active"):
                     reasons.add(nme)
+        if not sm:   # timed region shorter than the sampling period: take one reading now
+            try:
+                r = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                   capture_output=True, text=True, timeout=10).stdout.strip().split(",")
+                sm, mx = [float(r[0])], float(r[1])
+            except Exception:
+                pass
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
 
@@ -100,9 +112,10 @@ def run_ours(args):
     from zeroclone_b200 import _ffi
     from zeroclone_b200.evaluator import NetEvaluator, tower_flops_per_leaf
     from zeroclone_b200.search import TreeSearch
-    from zeroclone_b200.workloads import c4_roots_set_b
+    from zeroclone_b200.workloads import c4_roots_set_b, chess_roots_set_b
 
     wl = WORKLOADS[args.workload]
+    chess = wl["game"] == "chess"
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -116,19 +129,23 @@ def run_ours(args):
     sims = args.sims or wl["sims"]
     hbm_peak, tensor_peak, peak_src = read_peaks()
 
-    roots = c4_roots_set_b(trees, first_tree_id=rank * trees)
+    roots = (chess_roots_set_b if chess else c4_roots_set_b)(trees, first_tree_id=rank * trees)
     roots_pinned = torch.from_numpy(roots.view(np.uint8).reshape(trees, -1).copy()).pin_memory()
     roots_dev = roots_pinned.to(dev)
-    ts = TreeSearch(_ffi.GAME_C4, trees, sims, device=local)
+    ts = TreeSearch(_ffi.GAME_CHESS if chess else _ffi.GAME_C4, trees, sims, device=local)
     use_net = wl["evaluator"] == "value_net"
     ev = None
     if use_net:
-        from zeroclone_b200.models.connect4_value.network import ValueNetwork
+        if chess:
+            from zeroclone_b200.models.chess_value.network import ValueNetwork
+        else:
+            from zeroclone_b200.models.connect4_value.network import ValueNetwork
         torch.backends.cudnn.benchmark = True
         torch.manual_seed(0)
         ev = NetEvaluator(ValueNetwork().eval(), dev, torch.bfloat16, chunk=131072)
-        flops_leaf = tower_flops_per_leaf(2, 6, 7)
-    heur = {"c4_positional": _ffi.EVAL_C4_POSITIONAL, "c4_terminal": _ffi.EVAL_C4_TERMINAL}.get(wl["evaluator"])
+        flops_leaf = tower_flops_per_leaf(17, 8, 8) if chess else tower_flops_per_leaf(2, 6, 7)
+    heur = {"c4_positional": _ffi.EVAL_C4_POSITIONAL, "c4_terminal": _ffi.EVAL_C4_TERMINAL,
+            "chess_crude": _ffi.EVAL_CHESS_CRUDE}.get(wl["evaluator"])
     stream = torch.cuda.current_stream().cuda_stream
     phase_events = []   # (kind, start, end) CUDA events on the launching stream
 
@@ -224,9 +241,9 @@ def run_ours(args):
     # edge (16 B) and one N (4 B) per level.
     sims_done = trees * sims
     depth = cnt["sum_leaf_depth"] / max(1, cnt["simulations"])
-    kbar = 7.0
+    node_bytes = 16.0 * cnt["arena_slots_used"] / max(1, cnt["nodes"])       # measured mean node size (header+state+edges+moves)
     batches = sims_done / BATCH
-    tree_bytes_step = sims_done * (16 * (2 + kbar) + 4 + 20) + batches * (depth + 1) * (16 * (2 + kbar) + 2 * 20)
+    tree_bytes_step = sims_done * (node_bytes + 4 + 20) + batches * (depth + 1) * (node_bytes + 2 * 20)
     roofline_tree = {"bound": "hbm", "achieved": tree_bytes_step * args.steps / (tree_ms * 1e-3) / 1e9 if tree_ms else None,
                      "peak": hbm_peak, "unit": "GB/s", "traffic": None, "launches": n_tree,
                      "avg_launch_ms": tree_ms / max(1, n_tree), "share_of_step": tree_ms / ms}
@@ -254,7 +271,8 @@ def run_ours(args):
         "e2e": {"value": e2e_value, "unit": "sims/s", "ms_per_step": e2e_ms / args.steps,
                 "h2d_bytes_per_step": int(roots.nbytes), "d2h_bytes_per_step": int(sum(v.nbytes for v in out.values() if v is not None))},
         "gpu_launches": int(launches), "clocks": clocks,
-        "tree_stats": {"mean_leaf_depth": depth, "nodes_per_tree": cnt["nodes"] / trees},
+        "tree_stats": {"mean_leaf_depth": depth, "nodes_per_tree": cnt["nodes"] / trees, "mean_node_bytes": node_bytes,
+                       "algorithmic_bytes_per_sim": tree_bytes_step / sims_done},
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(args.workload, roots, sims, budget_s=args.cpu_budget)
@@ -274,6 +292,15 @@ def _port_worker(job):
     from oracle import zc_oracle as zo
     wl = WORKLOADS[workload]
     ext = None
+    if wl["game"] == "chess":
+        done = 0
+        for raw in rows:
+            st = zo.ChState.from_buffer_copy(raw)
+            zo.search(zo.GAME_CHESS, st, sims, C_UCT, BATCH, zo.EVAL_CHESS_CRUDE, zo.POLICY_FIRST)
+            done += sims
+            if time.time() > deadline:
+                break
+        return done
     if wl["evaluator"] == "value_net":
         import torch
         torch.set_num_threads(1)
@@ -304,8 +331,32 @@ def _ref_worker(job):
     """the UNMODIFIED reference search (oracle/_ref/mcts*.so) on one core"""
     workload, rows, sims, deadline = job
     from oracle import ref_harness as rh
-    mcts, _ = rh.ref_modules()
+    mcts, ref_chess = rh.ref_modules()
     wl = WORKLOADS[workload]
+    if wl["game"] == "chess":
+        import torch
+        torch.set_num_threads(1)
+        if wl["evaluator"] == "value_net":
+            from zeroclone_b200.models.chess_value.network import ValueNetwork
+            torch.manual_seed(0)
+            value = rh.TorchValue(ValueNetwork())
+        else:
+            pv = {'P': 1, 'N': 3, 'B': 3, 'R': 5, 'Q': 9, 'p': -1, 'n': -3, 'b': -3, 'r': -5, 'q': -9}
+
+            def crude(s, b):   # engine/value_functions.py:49-55
+                if b.check_win(s):
+                    return 1000
+                return (s.turn * -2 + 1) * sum(pv.get(chr(p), 0) for p in s.board)
+            value = rh.FnValue(crude)
+        done = 0
+        for raw in rows:
+            board = list(raw[:64])
+            st = ref_chess.State(board, raw[64], raw[65], bool(raw[66]), bool(raw[67]), bool(raw[68]), bool(raw[69]), [], [])
+            mcts.get_move(st, value, rh.first_policy, ref_chess, sims, C_UCT, BATCH)
+            done += sims
+            if time.time() > deadline:
+                break
+        return done
     if wl["evaluator"] == "value_net":
         import torch
         torch.set_num_threads(1)
@@ -335,7 +386,10 @@ def _cpu_pool_run(worker, workload, roots, sims, budget_s, trees_per_core=None):
     returns (sims/s aggregate, cores, sample description)."""
     import multiprocessing as mp
     cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
-    rows = [(int(r["x"]), int(r["o"]), int(r["turn"])) for r in roots]
+    if WORKLOADS[workload]["game"] == "chess":
+        rows = [r.tobytes() for r in roots]
+    else:
+        rows = [(int(r["x"]), int(r["o"]), int(r["turn"])) for r in roots]
     per = max(1, len(rows) // cores)
     ctx = mp.get_context("fork")
     t0 = time.time()
@@ -367,11 +421,11 @@ def run_reference(args):
         return
     import numpy as np  # noqa: F401
     from oracle.ref_harness import ref_available
-    from zeroclone_b200.workloads import c4_roots_set_b
+    from zeroclone_b200.workloads import c4_roots_set_b, chess_roots_set_b
     wl = WORKLOADS[args.workload]
     trees = args.trees or wl["trees"]
     sims = args.sims or wl["sims"]
-    roots = c4_roots_set_b(min(trees, 4096))
+    roots = (chess_roots_set_b if wl["game"] == "chess" else c4_roots_set_b)(min(trees, 4096))
     worker, kind = (_ref_worker, "reference") if ref_available() else (_port_worker, "port")
     per_step = max(2.0, min(20.0, 120.0 / (args.steps + args.warmup)))
     vals, sample, cores = [], "", 0

@@ -59,3 +59,41 @@ def c4_roots_set_b(n: int, first_tree_id: int = 0) -> np.ndarray:
                 break
         out[i] = (bb[0], bb[1], turn, 0)
     return out
+
+
+def chess_roots_set_a(n: int) -> np.ndarray:
+    s = _ffi.ChessState()
+    _ffi.check(_ffi.lib().zc_chess_init_state(C.byref(s)))
+    one = np.frombuffer(bytes(s), dtype=_ffi.CHESS_STATE_DTYPE)[0]
+    out = np.zeros(n, dtype=_ffi.CHESS_STATE_DTYPE)
+    out[:] = one
+    return out
+
+
+def chess_roots_set_b(n: int, first_tree_id: int = 0) -> np.ndarray:
+    L = _ffi.lib()
+    out = np.zeros(n, dtype=_ffi.CHESS_STATE_DTYPE)
+    mv = (_ffi.ChessMove * _ffi.MAX_MOVES)()
+    for i in range(n):
+        tid = first_tree_id + i
+        rng = np.random.Generator(np.random.PCG64(1234 + tid))
+        plies = tid % 13
+        while True:
+            s = _ffi.ChessState()
+            L.zc_chess_init_state(C.byref(s))
+            hist = [[], []]
+            for _ in range(plies):
+                k = L.zc_chess_legal_moves(C.byref(s), mv)
+                if k == 0:
+                    break
+                m = _ffi.ChessMove.from_buffer_copy(mv[int(rng.integers(k))])
+                hist[s.turn].insert(0, m)
+                nxt = _ffi.ChessState()
+                L.zc_chess_play_move(C.byref(s), C.byref(m), C.byref(nxt))
+                s = nxt
+            hw = (_ffi.ChessMove * max(1, len(hist[0])))(*hist[0])
+            hb = (_ffi.ChessMove * max(1, len(hist[1])))(*hist[1])
+            if not L.zc_chess_check_win(C.byref(s)) and not L.zc_chess_check_draw(C.byref(s), hw, len(hist[0]), hb, len(hist[1])):
+                break
+        out[i] = np.frombuffer(bytes(s), dtype=_ffi.CHESS_STATE_DTYPE)[0]
+    return out
