@@ -14,9 +14,9 @@ with torch.no_grad():
     ref = model(x[:8192]).view(-1)
 fl = tower_flops_per_leaf(2, 6, 7)
 for dtype in (torch.bfloat16, torch.float16):
-    for rfp32 in (False, True):
+    for rfp32 in (False,):
         for chunk in (8192, 32768, 131072):
-            ev = NetEvaluator(model, "cuda", dtype, chunk=chunk, residual_fp32=rfp32)
+            ev = NetEvaluator(model, "cuda", dtype, chunk=chunk)
             xd = x.to("cuda", dtype)
             err = (ev(xd[:8192]).cpu() - ref).abs()
             for _ in range(2):

@@ -28,13 +28,11 @@ def _fold(conv: nn.Conv2d, bn: nn.BatchNorm2d) -> Tuple[torch.Tensor, torch.Tens
 class NetEvaluator:
     """values = tanh(head(res(stem(planes))))  for planes[B, C, H, W] in `dtype`; returns float32[B]."""
 
-    def __init__(self, model: nn.Module, device="cuda", dtype: torch.dtype = torch.bfloat16, chunk: int = 32768,
-                 residual_fp32: bool = False):
+    def __init__(self, model: nn.Module, device="cuda", dtype: torch.dtype = torch.bfloat16, chunk: int = 131072):
         model = model.eval()
         self.device = torch.device(device)
         self.dtype = dtype
         self.chunk = chunk
-        self.residual_fp32 = residual_fp32
         self.in_planes = model.stem[0].in_channels
         cl = torch.channels_last
 
@@ -52,22 +50,28 @@ class NetEvaluator:
 
     @torch.inference_mode()
     def _forward_chunk(self, planes: torch.Tensor) -> torch.Tensor:
+        # cuDNN runtime-fused conv + bias (+ residual) + ReLU: one kernel per convolution, no separate
+        # elementwise passes over the 1.4 GB activation tensor (they were 2/3 of the forward time,
+        # profiles/r1_launches_c4_value_net_summary.csv).
+        one = [1, 1]
+        x = planes.contiguous(memory_format=torch.channels_last)
+        x = torch.cudnn_convolution_relu(x, self.stem[0], self.stem[1], one, one, one, 1)
+        for w1, b1, w2, b2 in self.blocks:
+            y = torch.cudnn_convolution_relu(x, w1, b1, one, one, one, 1)
+            x = torch.cudnn_convolution_add_relu(y, w2, x, 1.0, b2, one, one, one, 1)     # relu(conv(y) + x + b)
+        pooled = x.float().mean(dim=(2, 3))
+        return torch.tanh(torch.addmm(self.lin_b, pooled, self.lin_w)).view(-1)
+
+    @torch.inference_mode()
+    def forward_unfused(self, planes: torch.Tensor) -> torch.Tensor:
+        """The same network as separate conv / add / relu calls (kept for A/B timing)."""
         x = planes.contiguous(memory_format=torch.channels_last)
         x = F.relu_(F.conv2d(x, self.stem[0], self.stem[1], padding=1))
-        if self.residual_fp32:
-            r = x.float()
-            for w1, b1, w2, b2 in self.blocks:
-                y = F.relu_(F.conv2d(x, w1, b1, padding=1))
-                y = F.conv2d(y, w2, b2, padding=1)
-                r = F.relu_(r.add_(y))
-                x = r.to(self.dtype)
-            pooled = r.mean(dim=(2, 3))
-        else:
-            for w1, b1, w2, b2 in self.blocks:
-                y = F.relu_(F.conv2d(x, w1, b1, padding=1))
-                y = F.conv2d(y, w2, b2, padding=1)
-                x = F.relu_(y.add_(x))
-            pooled = x.float().mean(dim=(2, 3))
+        for w1, b1, w2, b2 in self.blocks:
+            y = F.relu_(F.conv2d(x, w1, b1, padding=1))
+            y = F.conv2d(y, w2, b2, padding=1)
+            x = F.relu_(y.add_(x))
+        pooled = x.float().mean(dim=(2, 3))
         return torch.tanh(torch.addmm(self.lin_b, pooled, self.lin_w)).view(-1)
 
     @torch.inference_mode()
