@@ -92,3 +92,28 @@ def test_chess_engine_with_network_evaluator_runs():
     res = eng.play_mcts_parallel(range(6), simulations=96, c=1.4)
     assert set(res) == set(range(6)) and all(r is None for r in res.values())
     assert all(len(h.states) == 2 for h in eng.history)
+
+
+def test_selfplay_refill_and_training_cycle(tmp_path, monkeypatch):
+    """simulate_games refill semantics (train.py:151-170) + one training cycle writing latest.pth"""
+    import importlib.util
+    import torch
+    from zeroclone_b200.engine import Engine
+    from zeroclone_b200.models import core
+    from zeroclone_b200.selfplay import simulate_games
+    eng = Engine({"game": "connect4", "backend": "c4_backend", "value_function": "network_latest", "threads": 8,
+                  "mcts": {"simulations": 32, "c_puct": 1.4}, "value": {"model_type": "connect4_value", "batch_size": 256}})
+    sp = simulate_games(eng, 20)
+    assert len(sp["results"]) == 20 and all(r in (-1, 0, 1) for r in sp["results"])
+    assert len(eng.states) == 20 and sp["games_per_hour"] > 0
+    x, y = eng.get_dataset()
+    assert len(x) == sum(len(h.states) for h in eng.history)
+    spec = importlib.util.spec_from_file_location("zc_train", os.path.join(REPO, "scripts", "train.py"))
+    tr = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(tr)
+    monkeypatch.setattr(core, "_ROOT", tmp_path)
+    (tmp_path / "connect4_value").mkdir()
+    loss = tr.train_and_save_latest("connect4_value", eng.values[0].model, x, y, epochs=1, lr=1e-3, batch_size=64,
+                                    device=torch.device("cuda", 0), rank=0, world=1)
+    assert np.isfinite(loss) and (tmp_path / "connect4_value" / "latest.pth").exists()
+    assert tr.schedule_hyperparams(0)["simulations"] == 100 and tr.schedule_hyperparams(30)["simulations"] == 800
