@@ -208,6 +208,28 @@ int zc_chess_perft(int device, const zc_chess_state *root, int depth, uint64_t *
  * bit 1 = check_draw */
 int zc_c4_rules_batch(int device, const zc_c4_state *states, int n, uint8_t *cols /* [n][8] */, int32_t *flags);
 
+/* ---- device-resident self-play step (Engine.play_move + _evaluate for every game at once,
+ * engine.py:98-108,148-153; the loop of scripts/train.py:151-170 keeps its roots on the device) ---- */
+
+/* game results as Engine._evaluate reports them, plus "still running" */
+#define ZC_RESULT_ONGOING 2
+
+/* After a search: for every tree whose `dev_active[i]` is non-zero, take the chosen root move
+ * (most-visited child, mcts.cpp:150-155), apply it to dev_states[i] (zc_c4_state / zc_chess_state
+ * records in device memory, the array that was given to zc_search_set_roots_dev), and evaluate the new
+ * position: check_win -> new.turn*2-1, check_draw -> 0, else ZC_RESULT_ONGOING.
+ * Chess: dev_hist holds each side's moves [n][2][hist_cap] in playing order (zc_chess_move), dev_hist_len
+ * [n][2]; both are updated (chess_backend.cpp:374) and used for the repetition rule (:148-180,434-438);
+ * the fifty-ply counter lives in the state record.  C4: pass NULL for both.
+ * host_results[n] (int32) and host_moves[n] receive the result and the move played (inactive trees:
+ * ZC_RESULT_ONGOING and a zero move).  Synchronises stream. */
+int zc_search_advance(zc_search *h, void *dev_states, const uint8_t *dev_active, zc_chess_move *dev_hist,
+                      int32_t *dev_hist_len, int hist_cap, int32_t *host_results, zc_chess_move *host_moves,
+                      void *stream);
+
+/* state_to_tensor for many packed states at once (host buffers): out[n][C][H][W] float32 */
+int zc_states_to_tensor(int game, const void *states, int n, float *out);
+
 #ifdef __cplusplus
 }
 #endif

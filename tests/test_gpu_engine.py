@@ -117,3 +117,74 @@ def test_selfplay_refill_and_training_cycle(tmp_path, monkeypatch):
                                     device=torch.device("cuda", 0), rank=0, world=1)
     assert np.isfinite(loss) and (tmp_path / "connect4_value" / "latest.pth").exists()
     assert tr.schedule_hyperparams(0)["simulations"] == 100 and tr.schedule_hyperparams(30)["simulations"] == 800
+
+
+@pytest.mark.parametrize("game", ["connect4", "chess"])
+def test_device_selfplay_matches_engine_host_loop(game):
+    """Device-resident self-play (advance kernel: apply move + win/draw incl. 50-ply and repetition) must
+    play exactly the games the Engine host loop plays (deterministic evaluator + policy)."""
+    from zeroclone_b200.engine import Engine
+    from zeroclone_b200.policy_functions import Policy
+    from zeroclone_b200.selfplay import DeviceSelfPlay, simulate_games
+    from zeroclone_b200.value_functions import Value
+    n, sims = 6, 40
+    cfg = {"game": game, "backend": "c4_backend" if game == "connect4" else "chess_backend", "threads": n,
+           "value_function": "c4_positional" if game == "connect4" else "crude_chess_score", "policy_functions": "first",
+           "mcts": {"simulations": sims, "c_puct": 1.4}}
+    eng = Engine(cfg)
+    assert eng.policy.name == "first"
+    max_plies = 60 if game == "chess" else 43
+    for ply in range(max_plies):                 # chess: bounded number of plies, games need not finish
+        unfinished = [i for i in range(n) if eng.history[i].result is None]
+        if not unfinished:
+            break
+        eng.play_mcts_parallel(unfinished, simulations=sims, c=1.4)
+    sp = DeviceSelfPlay(eng.backend, Value(cfg["value_function"]), Policy("first"), n_slots=n)
+    if game == "connect4":
+        out = sp.play(n, sims, 1.4)
+        assert out["results"] == [h.result for h in eng.history]
+        for g in range(n):
+            want = np.array([eng.backend.pack_state(s) for s in eng.history[g].states], dtype=eng.backend.STATE_DTYPE)
+            assert np.array_equal(np.stack(out["trajectories"][g]), want), g
+        x, y = eng.get_dataset()
+        assert np.array_equal(out["dataset"][0], x) and np.array_equal(out["dataset"][1], y)
+    else:
+        # identical games => every slot plays the same line; run the device loop until the first game ends or 60 plies
+        ref_states = eng.history[0].states
+        import ctypes as C
+        import torch
+        from zeroclone_b200 import _ffi, mcts
+        dev = torch.device("cuda", 0)
+        rec = np.zeros(1, dtype=eng.backend.STATE_DTYPE)
+        rec[0] = eng.backend.pack_state(ref_states[0])
+        roots = torch.from_numpy(np.repeat(rec, n).view(np.uint8).reshape(n, -1).copy()).to(dev)
+        hist = torch.zeros((n, 2, 512, 8), dtype=torch.uint8, device=dev)
+        hlen = torch.zeros((n, 2), dtype=torch.int32, device=dev)
+        ones = torch.ones(n, dtype=torch.uint8, device=dev)
+        ts = mcts.searcher(_ffi.GAME_CHESS, n, sims)
+        for ply in range(1, len(ref_states)):
+            ts.set_roots_dev(roots.data_ptr(), n)
+            ts.run(sims, 1.4, 32, _ffi.EVAL_CHESS_CRUDE, _ffi.POLICY_FIRST)
+            res = np.zeros(n, dtype=np.int32)
+            mv = np.zeros(n, dtype=_ffi.CHESS_MOVE_DTYPE)
+            _ffi.check(_ffi.lib().zc_search_advance(ts._h, roots.data_ptr(), ones.data_ptr(), hist.data_ptr(), hlen.data_ptr(), 512,
+                                                   res.ctypes.data_as(C.c_void_p), mv.ctypes.data_as(C.c_void_p), None))
+            got = roots.cpu().numpy().view(eng.backend.STATE_DTYPE).reshape(n)[0]
+            want = eng.backend.pack_state(ref_states[ply])
+            assert got.tobytes() == want.tobytes(), ply
+            host_result = eng._evaluate(ref_states[ply])
+            assert int(res[0]) == (_ffi.RESULT_ONGOING if host_result is None else host_result), ply
+        assert int(hlen.sum().item()) == n * (len(ref_states) - 1)
+
+
+def test_device_selfplay_refill_and_network():
+    from zeroclone_b200.games.connect4 import c4_backend
+    from zeroclone_b200.policy_functions import Policy
+    from zeroclone_b200.selfplay import DeviceSelfPlay
+    from zeroclone_b200.value_functions import Value
+    sp = DeviceSelfPlay(c4_backend, Value("network_latest", model_type="connect4_value"), Policy(), n_slots=16)
+    out = sp.play(40, 32, 1.4, seed=3)
+    assert len(out["results"]) == 40 and all(r in (-1, 0, 1) for r in out["results"])
+    x, y = out["dataset"]
+    assert x.shape[1:] == (2, 6, 7) and len(x) == len(y) == sum(len(t) for t in out["trajectories"])
+    assert out["games_per_hour"] > 0

@@ -14,6 +14,7 @@ EVAL_C4_TERMINAL, EVAL_C4_POSITIONAL, EVAL_CHESS_CRUDE, EVAL_EXTERNAL, EVAL_C4_R
 POLICY_FIRST, POLICY_LAST, POLICY_RANDOM = 0, 1, 2
 ZC_OK, ZC_EINVAL, ZC_ENODEVICE, ZC_ECUDA, ZC_ECAPACITY, ZC_ESTATE = 0, -1, -2, -3, -4, -5
 MAX_MOVES = 256
+RESULT_ONGOING = 2
 PLANE_BF16, PLANE_F32, PLANE_F16 = 0, 1, 2
 
 
@@ -100,6 +101,8 @@ def lib() -> C.CDLL:
     L.zc_chess_legal_moves_batch.argtypes = [i32, vp, i32, vp, vp, vp]
     L.zc_chess_perft.argtypes = [i32, vp, i32, vp]
     L.zc_c4_rules_batch.argtypes = [i32, vp, i32, vp, vp]
+    L.zc_search_advance.argtypes = [vp, vp, vp, vp, vp, i32, vp, vp, vp]
+    L.zc_states_to_tensor.argtypes = [i32, vp, i32, vp]
     assert C.sizeof(RootResult) == ROOT_RESULT_DTYPE.itemsize == 48, (C.sizeof(RootResult), ROOT_RESULT_DTYPE.itemsize)
     assert C.sizeof(C4State) == C4_STATE_DTYPE.itemsize == 24
     assert C.sizeof(ChessState) == CHESS_STATE_DTYPE.itemsize == 72

@@ -11,7 +11,7 @@ struct ChessGame {
     static constexpr int SS = 2;             // four bit planes = 32 bytes
     static constexpr int FIRST_SLOTS = 32;   // header + state + first 29 edges in one warp load
     static constexpr int PLANE_ELEMS = 17 * 64;
-    static constexpr int MOVE_SCRATCH = 224; // >= 218 moves, multiple of 8
+    static constexpr int MOVE_SCRATCH = chess::MAX_PSEUDO;   // pseudo-legal staging (>= 218 legal), multiple of 8
 
     struct Ctx {
         uint16_t* moves;   // this lane's move buffer

@@ -173,8 +173,17 @@ ZC_HD uint16_t pack_move(int from, int to) { return (uint16_t)(from | (to << 6))
 ZC_HD int move_from(uint16_t m) { return m & 63; }
 ZC_HD int move_to(uint16_t m) { return (m >> 6) & 63; }
 
-// chess_backend.cpp:184-360.  Writes the legal moves, in the reference's order, to out[]
-// (if non-null) and returns their number (<= 218).
+// chess_backend.cpp:184-360.  Writes the legal moves, in the reference's order, to out[] (room for
+// MAX_PSEUDO entries, never null) and returns their number (<= 218).
+//
+// Pass 1 emits the pseudo-legal moves in the reference's scan order (:203-342).  Pass 2 is the
+// reference's stable legality filter (:345-358) with ONE call site of the attack test and an exact
+// shortcut: if the mover is not in check, a non-king piece that does not stand on a rank, file or
+// diagonal through its king cannot expose the king by leaving its square (its destination can only
+// block lines, a capture only removes an attacker), so such a move is legal without testing.
+constexpr int MAX_PSEUDO = 256;
+constexpr uint16_t MOVE_KING_FLAG = 1u << 12;
+
 ZC_HD int generate(const Board& b, int turn, uint16_t* out) {
     if (insufficient_material(b)) return 0;
     const Sets s = derive(b, turn);
@@ -186,25 +195,19 @@ ZC_HD int generate(const Board& b, int turn, uint16_t* out) {
         const int sq = zc_ctz64(movers);
         movers &= movers - 1;
         const int type = piece_at(b, sq) & 7, r = sq >> 3, c = sq & 7;
-        const uint64_t me = bit(sq);
         if (type == PAWN) {                                             // :213-252
             const int dir = turn == 0 ? -1 : 1, home = turn == 0 ? 6 : 1;
             const int nr = r + dir;
             if (nr >= 0 && nr < 8) {
                 const int one = nr * 8 + c;
                 if (empty >> one & 1) {
-                    if (move_keeps_king_safe(s, turn, sq, one, false)) { if (out) out[n] = pack_move(sq, one); ++n; }
+                    out[n++] = pack_move(sq, one);
                     const int two = one + dir * 8;
-                    if (r == home && (empty >> two & 1))
-                        if (move_keeps_king_safe(s, turn, sq, two, false)) { if (out) out[n] = pack_move(sq, two); ++n; }
+                    if (r == home && (empty >> two & 1)) out[n++] = pack_move(sq, two);
                 }
-                for (int dc = -1; dc <= 1; dc += 2) {
-                    const int cc = c + dc;
-                    if (cc < 0 || cc > 7) continue;
-                    const int t = nr * 8 + cc;
-                    if ((s.enemy & ~s.e_king) >> t & 1)
-                        if (move_keeps_king_safe(s, turn, sq, t, false)) { if (out) out[n] = pack_move(sq, t); ++n; }
-                }
+                const uint64_t capturable = s.enemy & ~s.e_king;
+                if (c > 0 && (capturable >> (one - 1) & 1)) out[n++] = pack_move(sq, one - 1);
+                if (c < 7 && (capturable >> (one + 1) & 1)) out[n++] = pack_move(sq, one + 1);
             }
         } else if (type == KNIGHT || type == KING) {                    // :255-275, :322-340
             const bool is_king = type == KING;
@@ -220,23 +223,43 @@ ZC_HD int generate(const Board& b, int turn, uint16_t* out) {
                 const int rr = r + dr, cc = c + dc;
                 if (rr < 0 || rr > 7 || cc < 0 || cc > 7) continue;
                 const int t = rr * 8 + cc;
-                if (!(targets_ok >> t & 1)) continue;
-                if (move_keeps_king_safe(s, turn, sq, t, is_king)) { if (out) out[n] = pack_move(sq, t); ++n; }
+                if (targets_ok >> t & 1) out[n++] = (uint16_t)(pack_move(sq, t) | (is_king ? MOVE_KING_FLAG : 0));
             }
         } else if (type == BISHOP || type == ROOK || type == QUEEN) {   // :278-319
             const int d0 = type == ROOK ? 4 : 0, d1 = type == BISHOP ? 4 : 8;
+            const uint64_t me = bit(sq);
             for (int d = d0; d < d1; ++d) {
                 uint64_t tg = ray_dir(d, me, empty) & targets_ok;
                 const bool asc = dir_ascending(d);
                 while (tg) {                                            // outward = toward/away from index 0
                     const int t = asc ? zc_ctz64(tg) : 63 - zc_clz64(tg);
                     tg &= ~bit(t);
-                    if (move_keeps_king_safe(s, turn, sq, t, false)) { if (out) out[n] = pack_move(sq, t); ++n; }
+                    out[n++] = pack_move(sq, t);
                 }
             }
         }
     }
-    return n;
+    // ---- pass 2: legality filter, stable, in place
+    if (!s.own_king) {                       // a side without a king is never "in check"
+        for (int i = 0; i < n; ++i) out[i] &= 0x0FFF;
+        return n;
+    }
+    const int ksq = zc_ctz64(s.own_king);    // find_king: the first king in index order (:68-81)
+    const int kr = ksq >> 3, kc = ksq & 7;
+    const bool checked = square_attacked(turn, ksq, s.occ, s.e_pawn, s.e_knight, s.e_bishop | s.e_queen,
+                                         s.e_rook | s.e_queen, s.e_king);
+    int m = 0;
+    for (int i = 0; i < n; ++i) {
+        const uint16_t mv = out[i];
+        const int from = mv & 63, to = (mv >> 6) & 63;
+        const bool king_moves = (mv & MOVE_KING_FLAG) != 0;
+        const int dr = (from >> 3) - kr, dc = (from & 7) - kc;
+        const bool aligned = dr == 0 || dc == 0 || dr == dc || dr == -dc;
+        bool ok = true;
+        if (checked || king_moves || aligned) ok = move_keeps_king_safe(s, turn, from, to, king_moves);
+        if (ok) out[m++] = (uint16_t)(mv & 0x0FFF);
+    }
+    return m;
 }
 
 // chess_backend.cpp:364-400 on the board planes; flags in/out through `misc`.

@@ -118,7 +118,7 @@ extern "C" int zc_chess_from_fen(const char* fen, zc_chess_state* out) {
 extern "C" int zc_chess_legal_moves(const zc_chess_state* s, zc_chess_move* out) {
     if (!s || !out) return fail(ZC_EINVAL, "NULL argument");
     const chess::Board b = board_of(*s);
-    uint16_t mv[ChessGame::MOVE_SCRATCH];
+    uint16_t mv[chess::MAX_PSEUDO];
     const int n = chess::generate(b, s->turn ? 1 : 0, mv);
     for (int i = 0; i < n; ++i) out[i] = decode_move(b, mv[i]);
     return n;
@@ -148,7 +148,8 @@ extern "C" int zc_chess_check_win(const zc_chess_state* s) {
     if (!s) return fail(ZC_EINVAL, "NULL argument");
     const chess::Board b = board_of(*s);
     const int turn = s->turn ? 1 : 0;
-    return chess::generate(b, turn, nullptr) == 0 && chess::in_check(b, turn) ? 1 : 0;
+    uint16_t mv[chess::MAX_PSEUDO];
+    return chess::generate(b, turn, mv) == 0 && chess::in_check(b, turn) ? 1 : 0;
 }
 
 // chess_backend.cpp:148-180: some prefix of the (most-recent-first) list is >= 3 repeats of a period >= 2
@@ -176,7 +177,8 @@ extern "C" int zc_chess_check_draw(const zc_chess_state* s, const zc_chess_move*
         return fail(ZC_EINVAL, "bad argument");
     const chess::Board b = board_of(*s);
     const int turn = s->turn ? 1 : 0;
-    if (chess::generate(b, turn, nullptr) == 0 && !chess::in_check(b, turn)) return 1;   // stalemate branch (:419-427)
+    uint16_t mv[chess::MAX_PSEUDO];
+    if (chess::generate(b, turn, mv) == 0 && !chess::in_check(b, turn)) return 1;   // stalemate branch (:419-427)
     if (s->fifty_move_rule_counter >= 50) return 1;                                       // plies, :429
     if (repeated_prefix(hist_white, n_white, 2, 3) && repeated_prefix(hist_black, n_black, 2, 3)) return 1;
     return 0;
@@ -219,7 +221,8 @@ __global__ void k_perft_count(const PerftState* __restrict__ frontier, unsigned 
                               unsigned long long* __restrict__ total) {
     const unsigned long long t = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
     unsigned long long mine = 0;
-    if (t < n) mine = (unsigned long long)chess::generate(frontier[t].b, (int)(frontier[t].misc & 1u), nullptr);
+    uint16_t mv[chess::MAX_PSEUDO];
+    if (t < n) mine = (unsigned long long)chess::generate(frontier[t].b, (int)(frontier[t].misc & 1u), mv);
     for (int d = 16; d >= 1; d >>= 1) mine += __shfl_xor_sync(0xFFFFFFFFu, mine, d);
     if ((threadIdx.x & 31) == 0 && mine) atomicAdd(total, mine);
 }
@@ -346,5 +349,164 @@ extern "C" int zc_c4_rules_batch(int device, const zc_c4_state* states, int n, u
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaMemcpy(cols, dc.p, (size_t)n * 8, cudaMemcpyDeviceToHost));
     CUDA_TRY(cudaMemcpy(flags, df.p, sizeof(int32_t) * (size_t)n, cudaMemcpyDeviceToHost));
+    return ZC_OK;
+}
+
+// ------------------------------------------------------------------------------------------ self-play step
+__device__ static int root_best_edge(const uint4* arena, int k, int ss) {
+    int best = -1, best_n = -1;
+    for (int i = 0; i < k; ++i) {
+        const uint4 e = arena[1 + ss + i];
+        if (e.w && (int)e.z > best_n) { best_n = (int)e.z; best = i; }
+    }
+    return best;
+}
+
+__global__ void k_advance_c4(const uint4* __restrict__ arena_all, uint64_t arena_slots, int n, zc_c4_state* __restrict__ states,
+                             const uint8_t* __restrict__ active, int32_t* __restrict__ results, zc_chess_move* __restrict__ moves) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    zc_chess_move mv = {0, 0, 0, 0, 0.f};
+    int result = ZC_RESULT_ONGOING;
+    if (active[t]) {
+        const uint4* arena = arena_all + (uint64_t)t * arena_slots;
+        const int k = (int)hdr_k(arena[0]);
+        const int best = root_best_edge(arena, k, C4Game::SS);
+        if (best >= 0) {
+            zc_c4_state s = states[t];
+            c4::State r;
+            r.cur = s.turn == 0 ? s.x : s.o;
+            r.opp = s.turn == 0 ? s.o : s.x;
+            const int col = c4::move_col(c4::legal_mask(r), best);
+            const c4::State nx = c4::play(r, col);
+            zc_c4_state o;
+            o.turn = 1 - s.turn;
+            o.x = s.turn == 0 ? nx.opp : nx.cur;
+            o.o = s.turn == 0 ? nx.cur : nx.opp;
+            o.reserved = 0;
+            states[t] = o;
+            mv.fr = (uint8_t)col;
+            if (c4::check_win(nx)) result = o.turn * 2 - 1;          // engine.py:149-150
+            else if (c4::check_draw(nx)) result = 0;
+        }
+    }
+    results[t] = result;
+    moves[t] = mv;
+}
+
+// chess_backend.cpp:148-180 on a history kept in playing order: L[i] = hist[len-1-i] (most recent first)
+__device__ static bool dev_repeated_prefix(const zc_chess_move* hist, int n, int* pi) {
+    if (n < 6) return false;
+    auto eq = [&](int a, int b) {
+        const zc_chess_move x = hist[n - 1 - a], y = hist[n - 1 - b];
+        return x.fr == y.fr && x.fc == y.fc && x.tr == y.tr && x.tc == y.tc && x.value == y.value;
+    };
+    pi[0] = 0;
+    for (int i = 1, j = 0; i < n; ++i) {
+        while (j > 0 && !eq(i, j)) j = pi[j - 1];
+        if (eq(i, j)) ++j;
+        pi[i] = j;
+    }
+    for (int i = 0; i < n; ++i) {
+        const int len = i + 1, period = len - pi[i];
+        if (period >= 2 && len % period == 0 && len / period >= 3) return true;
+    }
+    return false;
+}
+
+__global__ void k_advance_chess(const uint4* __restrict__ arena_all, uint64_t arena_slots, int n,
+                                zc_chess_state* __restrict__ states, const uint8_t* __restrict__ active,
+                                zc_chess_move* __restrict__ hist, int32_t* __restrict__ hist_len, int hist_cap,
+                                int* __restrict__ kmp_scratch, uint16_t* __restrict__ move_scratch,
+                                int32_t* __restrict__ results, zc_chess_move* __restrict__ moves) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    zc_chess_move mv = {0, 0, 0, 0, 0.f};
+    int result = ZC_RESULT_ONGOING;
+    if (active[t]) {
+        const uint4* arena = arena_all + (uint64_t)t * arena_slots;
+        const int k = (int)hdr_k(arena[0]);
+        const int best = root_best_edge(arena, k, ChessGame::SS);
+        if (best >= 0) {
+            const zc_chess_state s = states[t];
+            const chess::Board b = ChessGame::load_state(arena + 1);
+            const uint16_t m = ChessGame::move_at(arena, k, best);
+            mv = decode_move(b, m);
+            const int from = chess::move_from(m), to = chess::move_to(m), turn = s.turn ? 1 : 0;
+            uint32_t nm;
+            const chess::Board nb = chess::play(b, misc_of(s), from, to, nm);
+            zc_chess_state o = s;
+            for (int i = 0; i < 64; ++i) o.board[i] = chess::char_of_code(chess::piece_at(nb, i));
+            o.turn = (uint8_t)(nm & chess::MISC_TURN);
+            o.w_ck = (nm & chess::MISC_WCK) != 0;
+            o.w_cq = (nm & chess::MISC_WCQ) != 0;
+            o.b_ck = (nm & chess::MISC_BCK) != 0;
+            o.b_cq = (nm & chess::MISC_BCQ) != 0;
+            o.fifty_move_rule_counter = chess::resets_fifty(b, from, to) ? 0 : (uint8_t)(s.fifty_move_rule_counter + 1);
+            states[t] = o;
+            // the mover's history grows by this move (hist_white.push_front / hist_black.push_front, :374)
+            zc_chess_move* hw = hist + ((size_t)t * 2 + 0) * hist_cap;
+            zc_chess_move* hb = hist + ((size_t)t * 2 + 1) * hist_cap;
+            int nw = hist_len[t * 2 + 0], nbk = hist_len[t * 2 + 1];
+            if (turn == 0) { if (nw < hist_cap) hw[nw++] = mv; hist_len[t * 2 + 0] = nw; }
+            else { if (nbk < hist_cap) hb[nbk++] = mv; hist_len[t * 2 + 1] = nbk; }
+            // _evaluate(new state): check_win, then check_draw (:404-441)
+            const int nturn = o.turn ? 1 : 0;
+            const int nmoves = chess::generate(nb, nturn, move_scratch + (size_t)t * chess::MAX_PSEUDO);
+            const bool chk = chess::in_check(nb, nturn);
+            if (nmoves == 0 && chk) result = nturn * 2 - 1;
+            else if (nmoves == 0) result = 0;                                        // stalemate / insufficient material
+            else if (o.fifty_move_rule_counter >= 50) result = 0;                    // plies, :429
+            else {
+                int* pi = kmp_scratch + (size_t)t * hist_cap;
+                if (dev_repeated_prefix(hw, nw, pi) && dev_repeated_prefix(hb, nbk, pi)) result = 0;
+            }
+        }
+    }
+    results[t] = result;
+    moves[t] = mv;
+}
+
+extern "C" int zc_search_advance(zc_search* h, void* dev_states, const uint8_t* dev_active, zc_chess_move* dev_hist,
+                                 int32_t* dev_hist_len, int hist_cap, int32_t* host_results, zc_chess_move* host_moves,
+                                 void* stream) {
+    if (int rc = check_handle(h)) return rc;
+    if (!dev_states || !dev_active || !host_results || !host_moves) return fail(ZC_EINVAL, "advance: NULL argument");
+    if (h->n_trees < 1) return fail(ZC_ESTATE, "no roots set");
+    CUDA_TRY(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int n = h->n_trees;
+    DevBuf dres, dmv, dkmp;
+    CUDA_TRY(cudaMalloc(&dres.p, sizeof(int32_t) * (size_t)n));
+    CUDA_TRY(cudaMalloc(&dmv.p, sizeof(zc_chess_move) * (size_t)n));
+    if (h->game == ZC_GAME_C4) {
+        k_advance_c4<<<(n + 127) / 128, 128, 0, st>>>(h->arena, h->arena_slots, n, (zc_c4_state*)dev_states, dev_active,
+                                                    (int32_t*)dres.p, (zc_chess_move*)dmv.p);
+    } else {
+        if (!dev_hist || !dev_hist_len || hist_cap < 8) return fail(ZC_EINVAL, "advance: chess needs history buffers");
+        CUDA_TRY(cudaMalloc(&dkmp.p, sizeof(int) * (size_t)n * hist_cap));
+        k_advance_chess<<<(n + 63) / 64, 64, 0, st>>>(h->arena, h->arena_slots, n, (zc_chess_state*)dev_states, dev_active,
+                                                    dev_hist, dev_hist_len, hist_cap, (int*)dkmp.p, h->scratch,
+                                                    (int32_t*)dres.p, (zc_chess_move*)dmv.p);
+    }
+    h->launches++;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(host_results, dres.p, sizeof(int32_t) * (size_t)n, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(host_moves, dmv.p, sizeof(zc_chess_move) * (size_t)n, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return ZC_OK;
+}
+
+extern "C" int zc_states_to_tensor(int game, const void* states, int n, float* out) {
+    if (!states || !out || n < 0) return fail(ZC_EINVAL, "bad argument");
+    if (game == ZC_GAME_C4) {
+        const zc_c4_state* s = (const zc_c4_state*)states;
+        for (int i = 0; i < n; ++i) zc_c4_to_tensor(s + i, out + (size_t)i * 84);
+    } else if (game == ZC_GAME_CHESS) {
+        const zc_chess_state* s = (const zc_chess_state*)states;
+        for (int i = 0; i < n; ++i) zc_chess_to_tensor(s + i, out + (size_t)i * 17 * 64);
+    } else {
+        return fail(ZC_EINVAL, "unknown game");
+    }
     return ZC_OK;
 }

@@ -37,3 +37,119 @@ def simulate_games(engine, total_games: int, simulations: Optional[int] = None, 
     dt = time.time() - t0
     return {"results": final, "moves": plies, "seconds": dt, "games_per_hour": len(final) / dt * 3600.0,
             "sims_per_sec": plies * sims / dt}
+
+
+class DeviceSelfPlay:
+    """Device-resident self-play: root states live in HBM between moves.
+
+    Per ply: gather the running games' roots (device) -> one batched search -> `zc_search_advance`
+    applies every tree's chosen move and evaluates the new position on the device (win / draw incl.
+    chess 50-ply counter and KMP repetition) -> scatter back.  The host only receives (move, result)
+    per game and a copy of the packed states for the dataset.  Refill semantics of
+    scripts/train.py:151-170: `n_slots` games in flight until `total_games` have been started.
+    Labels as Engine.get_dataset (engine.py:60-89): the final position -1, alternating backwards, draws 0.
+    """
+
+    def __init__(self, backend, value, policy, n_slots: int, device: int | None = None, batch_size: int = 32,
+                 hist_cap: int = 512):
+        import torch
+
+        from . import _ffi, mcts
+        self.torch, self._ffi, self._mcts = torch, _ffi, mcts
+        self.backend, self.value, self.policy = backend, value, policy
+        self.game = backend.ZC_GAME
+        self.n_slots, self.batch_size, self.hist_cap = n_slots, batch_size, hist_cap
+        self.device = torch.cuda.current_device() if device is None else device
+        self.kind, self.ev = value.device_spec(self.game)
+        self.pol = policy.device_policy
+        self.init_rec = self._pack(backend.create_init_state())
+
+    def _pack(self, state):
+        import numpy as np
+        rec = np.zeros(1, dtype=self.backend.STATE_DTYPE)
+        rec[0] = self.backend.pack_state(state)
+        return rec
+
+    def play(self, total_games: int, simulations: int, c: float = 1.4, seed: int = 0, record: bool = True) -> dict:
+        import ctypes as C
+
+        import numpy as np
+        torch, _ffi = self.torch, self._ffi
+        dev = torch.device("cuda", self.device)
+        n_slots = min(self.n_slots, total_games)
+        item = self.init_rec.dtype.itemsize
+        chess = self.game == _ffi.GAME_CHESS
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream().cuda_stream
+            states_all = torch.from_numpy(np.repeat(self.init_rec, n_slots).view(np.uint8).reshape(n_slots, item).copy()).to(dev)
+            hist_all = torch.zeros((n_slots, 2, self.hist_cap, 8), dtype=torch.uint8, device=dev) if chess else None
+            hlen_all = torch.zeros((n_slots, 2), dtype=torch.int32, device=dev) if chess else None
+            ts = self._mcts.searcher(self.game, n_slots, simulations, self.device)
+            slot_game = list(range(n_slots))              # game id played in each slot
+            started, finished = n_slots, 0
+            results = [None] * total_games
+            traj = [[self.init_rec[0].copy()] for _ in range(total_games)] if record else None
+            active = list(range(n_slots))
+            plies = 0
+            t0 = time.time()
+            while active:
+                idx = torch.tensor(active, dtype=torch.long, device=dev)
+                roots = states_all.index_select(0, idx).contiguous()
+                n = len(active)
+                ts.set_roots_dev(roots.data_ptr(), n, stream)
+                if self.kind == "builtin":
+                    ts.run(simulations, c, self.batch_size, self.ev, self.pol, seed + plies, stream)
+                else:
+                    ts.run_network(self.ev, simulations, c, self.batch_size, self.pol, seed + plies)
+                ones = torch.ones(n, dtype=torch.uint8, device=dev)
+                res = np.zeros(n, dtype=np.int32)
+                mv = np.zeros(n, dtype=_ffi.CHESS_MOVE_DTYPE)
+                if chess:
+                    hist = hist_all.index_select(0, idx).contiguous()
+                    hlen = hlen_all.index_select(0, idx).contiguous()
+                    _ffi.check(_ffi.lib().zc_search_advance(ts._h, roots.data_ptr(), ones.data_ptr(), hist.data_ptr(), hlen.data_ptr(),
+                                                           self.hist_cap, res.ctypes.data_as(C.c_void_p), mv.ctypes.data_as(C.c_void_p), stream))
+                    hist_all.index_copy_(0, idx, hist)
+                    hlen_all.index_copy_(0, idx, hlen)
+                else:
+                    _ffi.check(_ffi.lib().zc_search_advance(ts._h, roots.data_ptr(), ones.data_ptr(), None, None, 0,
+                                                           res.ctypes.data_as(C.c_void_p), mv.ctypes.data_as(C.c_void_p), stream))
+                plies += n
+                new_host = roots.cpu().numpy().view(self.init_rec.dtype).reshape(n) if record else None
+                refill = []
+                still = []
+                for j, slot in enumerate(active):
+                    g = slot_game[slot]
+                    if record:
+                        traj[g].append(new_host[j].copy())
+                    if res[j] == _ffi.RESULT_ONGOING:
+                        still.append(slot)
+                        continue
+                    results[g] = int(res[j])
+                    finished += 1
+                    if started < total_games:
+                        slot_game[slot] = started
+                        started += 1
+                        refill.append(j)
+                        still.append(slot)
+                states_all.index_copy_(0, idx, roots)
+                if refill:
+                    ridx = idx[torch.tensor(refill, dtype=torch.long, device=dev)]
+                    states_all[ridx] = torch.from_numpy(self.init_rec.view(np.uint8).reshape(1, item).copy()).to(dev)
+                    if chess:
+                        hlen_all[ridx] = 0
+                active = still
+            torch.cuda.synchronize()
+            dt = time.time() - t0
+        out = {"results": results, "moves": plies, "seconds": dt, "games_per_hour": total_games / dt * 3600.0,
+               "sims_per_sec": plies * simulations / dt}
+        if record:
+            lens = [len(t) for t in traj]
+            flat = np.concatenate([np.stack(t) for t in traj]) if traj else np.zeros(0, dtype=self.init_rec.dtype)
+            planes = np.zeros((len(flat),) + tuple(self.backend.TENSOR_SHAPE), dtype=np.float32)
+            _ffi.check(_ffi.lib().zc_states_to_tensor(self.game, flat.ctypes.data_as(C.c_void_p), len(flat),
+                                                      planes.ctypes.data_as(C.c_void_p)))
+            labels = np.concatenate([(0.0 if r == 0 else -1.0) * (-1.0) ** (np.arange(L)[::-1]) for r, L in zip(results, lens)])
+            out["dataset"] = (planes, labels.astype(np.float32))
+            out["trajectories"] = traj
+        return out
