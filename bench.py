@@ -274,6 +274,26 @@ def run_ours(args):
         "tree_stats": {"mean_leaf_depth": depth, "nodes_per_tree": cnt["nodes"] / trees, "mean_node_bytes": node_bytes,
                        "algorithmic_bytes_per_sim": tree_bytes_step / sims_done},
     }
+    if args.selfplay_games > 0:
+        # secondary half of the metric: self-play games/hour with the full move loop on the device
+        # (search, apply move, win/draw detection, refill); not part of the timed steps above
+        from zeroclone_b200.policy_functions import Policy
+        from zeroclone_b200.selfplay import DeviceSelfPlay
+        from zeroclone_b200.value_functions import Value
+        if chess:
+            from zeroclone_b200.games.chess import chess_backend as backend
+        else:
+            from zeroclone_b200.games.connect4 import c4_backend as backend
+        vname = "network_latest" if use_net else wl["evaluator"].replace("chess_crude", "crude_chess_score")
+        vkw = {"model_type": "chess_value" if chess else "connect4_value"} if use_net else {}
+        del ts
+        sp = DeviceSelfPlay(backend, Value(vname, **vkw), Policy("random"), n_slots=args.selfplay_games, device=local)
+        spo = sp.play(args.selfplay_games, sims, C_UCT, seed=rank, record=False)
+        gph = torch.tensor([spo["games_per_hour"]], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(gph, op=dist.ReduceOp.SUM)
+        line["selfplay"] = {"games_per_hour": float(gph[0]), "games": args.selfplay_games * world, "sims": sims, "policy": "random",
+                            "plies": spo["moves"], "seconds": spo["seconds"], "note": "device-resident loop (zc_search_advance), games in flight = games"}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(args.workload, roots, sims, budget_s=args.cpu_budget)
     if rank == 0:
@@ -456,6 +476,7 @@ def main():
     ap.add_argument("--trees", type=int, default=0, help="trees per GPU (default: the workload's)")
     ap.add_argument("--sims", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--selfplay-games", type=int, default=512, help="games of the games/hour side measurement (0 = skip)")
     ap.add_argument("--cpu-budget", type=float, default=15.0)
     args = ap.parse_args()
     if args.impl == "reference":

@@ -30,7 +30,7 @@ sys.path.insert(0, os.path.abspath(os.path.join(os.path.dirname(__file__), "..")
 from zeroclone_b200 import parallel  # noqa: E402
 from zeroclone_b200.engine import Engine  # noqa: E402
 from zeroclone_b200.models import core  # noqa: E402
-from zeroclone_b200.selfplay import simulate_games  # noqa: E402
+from zeroclone_b200.selfplay import DeviceSelfPlay  # noqa: E402
 
 _REPLAY_STATES: list = []
 _REPLAY_VALUES: list = []
@@ -81,7 +81,7 @@ def train_and_save_latest(model_type, model, states, values, *, epochs, lr, batc
     xs = torch.from_numpy(states).float().to(device)
     ys = torch.from_numpy(values).float().to(device).unsqueeze(1)
     n = len(xs)
-    steps = int(parallel.reduce_max([-(-n // batch_size)], device=device if device.type == "cuda" else "cpu")[0]) if n else 0
+    steps = int(parallel.reduce_max([-(-n // batch_size)])[0])
     total = 0.0
     for epoch in range(1, epochs + 1):
         perm = torch.randperm(n, device=device) if n else None
@@ -132,12 +132,13 @@ def full_training_run(config_name, *, cycles=30, batch_size=256, epochs=4, games
         my_games = len(parallel.shard_range(hp["games"], rank, world))
         if rank == 0:
             emit_stats(stage="cycle_start", cycle=cycle + 1, total_cycles=cycles, games_target=hp["games"], sims=hp["simulations"])
-        with timer("SELF-PLAY"):
-            sp = simulate_games(engine, my_games, on_game_done=(lambda done, tgt: emit_stats(
-                stage="game_done", cycle=cycle + 1, finished=done, target=tgt)) if rank == 0 else None)
+        with timer("SELF-PLAY"):          # device-resident: roots stay in HBM between moves, engine.threads games in flight
+            sp = DeviceSelfPlay(engine.backend, value, engine.policy, n_slots=engine.threads, device=local if device.type == "cuda" else None,
+                                batch_size=engine.batch_size).play(my_games, hp["simulations"], hp["c_puct"], seed=cycle * 1000003 + rank)
+            if rank == 0:
+                emit_stats(stage="game_done", cycle=cycle + 1, finished=len(sp["results"]), target=my_games)
         games_h = parallel.reduce_sum([sp["games_per_hour"]])[0]
-        with timer("DATASET BUILD"):
-            states_now, values_now = engine.get_dataset()
+        states_now, values_now = sp["dataset"]
         states, values = update_replay(states_now, values_now)
         if rank == 0:
             print(f"Replay buffer : {len(values):,} positions total (+{len(values_now)} this cycle); self-play {games_h:,.0f} games/hour")
@@ -148,6 +149,8 @@ def full_training_run(config_name, *, cycles=30, batch_size=256, epochs=4, games
         value._net = None          # self-play of the next cycle evaluates with the freshly trained weights
     if rank == 0:
         emit_stats(stage="train_done", cycle=cycles, loss=loss_acc / max(1, cycles), epochs=epochs)
+    if torch.distributed.is_available() and torch.distributed.is_initialized():
+        torch.distributed.destroy_process_group()
 
 
 if __name__ == "__main__":

@@ -42,15 +42,24 @@ def _active() -> bool:
     return dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
 
 
-def reduce_max(values: Iterable[float], device="cpu") -> List[float]:
-    t = torch.tensor(list(values), dtype=torch.float64, device=device)
+def _reduce_device(device):
+    """NCCL reduces device tensors only; gloo reduces host tensors."""
+    if device is not None:
+        return device
+    if _active() and dist.get_backend() == "nccl":
+        return torch.device("cuda", torch.cuda.current_device())
+    return "cpu"
+
+
+def reduce_max(values: Iterable[float], device=None) -> List[float]:
+    t = torch.tensor(list(values), dtype=torch.float64, device=_reduce_device(device))
     if _active():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     return t.tolist()
 
 
-def reduce_sum(values: Iterable[float], device="cpu") -> List[float]:
-    t = torch.tensor(list(values), dtype=torch.float64, device=device)
+def reduce_sum(values: Iterable[float], device=None) -> List[float]:
+    t = torch.tensor(list(values), dtype=torch.float64, device=_reduce_device(device))
     if _active():
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
     return t.tolist()
