@@ -12,6 +12,7 @@ struct C4Game {
     static constexpr int FIRST_SLOTS = 9;   // header + state + up to 7 edges: the whole node in one warp load
     static constexpr int PLANE_ELEMS = 84;  // 2 x 6 x 7 (c4_backend.py:52-61)
     static constexpr int MOVE_SCRATCH = 0;
+    static constexpr bool kCheapSpine = true;   // play + legal mask are a handful of instructions
     struct Ctx {};
     ZC_D static Ctx make_ctx(const SearchParams&, unsigned, int) { return Ctx(); }
 
@@ -38,6 +39,7 @@ struct C4Game {
         r.opp = __shfl_sync(FULL_MASK, s.opp, src);
         return r;
     }
+    ZC_HD static uint64_t state_key(const State& s, uint32_t) { return s.cur * 0x9E3779B97F4A7C15ull ^ (s.opp + 0xD1B54A32D192ED03ull) * 0xBF58476D1CE4E5B9ull; }
     ZC_HD static int move_slots(int) { return 0; }                    // moves are implied by the legal mask
     ZC_HD static void store_moves(Ctx&, uint4*, int) {}
     // state after the ei-th move (backend order) of `parent`

@@ -40,11 +40,10 @@ ZC_HD uint32_t order_of(int mask) {
 
 // c4_backend.py:49-50 -- a column is playable iff its TOP cell is empty (wins are ignored)
 ZC_HD int legal_mask(const State& s) {
-    const uint64_t free_top = ~(s.cur | s.opp) & TOPS;
-    int m = 0;
-#pragma unroll
-    for (int c = 0; c < COLS; ++c) m |= (int)((free_top >> (7 * c + 5)) & 1ull) << c;
-    return m;
+    // free top cells sit at bits 5, 12, ..., 47; (x >> 5) has them at 7c.  Multiplying by
+    // sum_c 2^(42-6c) moves bit 7c to 42+c; no two partial products share a position, so no carries.
+    const uint64_t free_top = (~(s.cur | s.opp) & TOPS) >> 5;
+    return (int)((free_top * 0x0000041041041040ull) >> 42) & 0x7F;
 }
 ZC_HD int n_moves(const State& s) { return zc_popc32((unsigned)legal_mask(s)); }
 // column of the idx-th move in backend (set-iteration) order

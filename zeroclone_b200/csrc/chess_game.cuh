@@ -11,6 +11,7 @@ struct ChessGame {
     static constexpr int SS = 2;             // four bit planes = 32 bytes
     static constexpr int FIRST_SLOTS = 32;   // header + state + first 29 edges in one warp load
     static constexpr int PLANE_ELEMS = 17 * 64;
+    static constexpr bool kCheapSpine = false;  // a chain node needs a full move generation: expand level by level
     static constexpr int MOVE_SCRATCH = chess::MAX_PSEUDO;   // pseudo-legal staging (>= 218 legal), multiple of 8
 
     struct Ctx {
@@ -50,6 +51,9 @@ struct ChessGame {
         r.p2 = __shfl_sync(FULL_MASK, s.p2, src);
         r.p3 = __shfl_sync(FULL_MASK, s.p3, src);
         return r;
+    }
+    ZC_HD static uint64_t state_key(const State& s, uint32_t misc) {
+        return (s.p0 * 0x9E3779B97F4A7C15ull) ^ (s.p1 * 0xBF58476D1CE4E5B9ull) ^ (s.p2 * 0x94D049BB133111EBull) ^ (s.p3 * 0xD1B54A32D192ED03ull) ^ misc;
     }
     ZC_HD static int move_slots(int k) { return (k + 7) >> 3; }
     // packed move i of the node at `node` (k moves): stored after the edges, 8 per slot

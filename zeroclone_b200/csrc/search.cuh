@@ -126,21 +126,24 @@ struct Leaf {
     uint32_t misc;
 };
 
-template <class G, bool kBuiltinEval>
-ZC_D bool select_expand(const SearchParams& p, typename G::Ctx& gx, uint4* __restrict__ arena, uint2* __restrict__ path,
-                        TreeCtl& ctl, int B, int lane, int& D_out, Leaf<G>& leaf) {
-    // ---- frozen descent (mcts.cpp:47-63)
+// Per-warp plan of one batch, in shared memory: where each chain level's leaves start in the
+// pending list and which leaf becomes the next chain node.  Level g is path level d0+g.
+struct WarpPlan {
+    int off[34];     // off[g] = index of the first leaf whose parent is chain level g; off[G] = B
+    int pleaf[34];   // pleaf[g] = lane of the leaf (child of level g) that is chain level g+1
+};
+
+// ---- frozen descent (mcts.cpp:47-63): root -> first node with untried moves (or without moves)
+template <class G>
+ZC_D bool descend(const SearchParams& p, const uint4* __restrict__ arena, uint2* __restrict__ path, TreeCtl& ctl, int lane,
+                  uint32_t& node_out, int& depth_out, uint4& hdr, typename G::State& st) {
     uint32_t node = 0;
     int depth = 0;
-    uint4 hdr;
-    typename G::State st;
-    uint32_t misc;
     for (;;) {
         const uint4* np = arena + node;
         uint4 v = make_uint4(0, 0, 0, 0);
         if (lane < G::FIRST_SLOTS) v = np[lane];
         hdr = shfl4(v, 0);
-        misc = hdr_misc(hdr);
         st = G::state_from_lanes(v);
         const int k = (int)hdr_k(hdr), nexp = (int)hdr_nexp(hdr);
         if (nexp < k || k == 0) break;
@@ -172,27 +175,172 @@ ZC_D bool select_expand(const SearchParams& p, typename G::Ctx& gx, uint4* __res
         ctl.sum_path_children += (unsigned)k;
         node = best_child;
         ++depth;
-        if ((uint32_t)depth + 34u >= p.path_cap) { ctl.status = -4; return false; }
+        if ((uint32_t)depth + 36u >= p.path_cap) { ctl.status = -4; return false; }
     }
+    node_out = node;
+    depth_out = depth;
+    return true;
+}
 
-    // ---- chain of expansions (mcts.cpp:65-78 applied batch_size times to frozen statistics)
-    uint32_t P = node;
+// lowest move index among the moves order(nexp) .. order(nexp+m-1) expanded at a node, and which j gives it
+ZC_D void lowest_fresh(int policy, int k, int nexp, int m, uint64_t nkey, int lane, int& e_star, int& j_star) {
+    if (policy == 0) { e_star = nexp; j_star = 0; return; }                   // first: ascending
+    if (policy == 1) { e_star = k - nexp - m; j_star = m - 1; return; }       // last: descending
+    int e = lane < m ? keyed_perm(k, nexp + lane, nkey) : 0x7FFFFFFF;
+    int mn = e;
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) mn = min(mn, __shfl_xor_sync(FULL_MASK, mn, d));
+    e_star = mn;
+    j_star = __ffs((int)__ballot_sync(FULL_MASK, e == mn)) - 1;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Chain of expansions, SPINE-FIRST variant for games whose rules are a few instructions
+// (G::kCheapSpine): the chain nodes ("spine": P, its lowest fresh child, that child's lowest
+// child, ...) are computed by the whole warp redundantly, then ALL batch_size leaves are created
+// in ONE lane-parallel step (lane i = pending[i]) instead of one step per chain level.
+// ---------------------------------------------------------------------------------------------
+template <class G, bool kBuiltinEval>
+ZC_D bool expand_spine(const SearchParams& p, typename G::Ctx& gx, uint4* __restrict__ arena, uint2* __restrict__ path,
+                       TreeCtl& ctl, int B, int lane, uint32_t P, const uint4& hdr, const typename G::State& Pst,
+                       int d0, WarpPlan& wp, int& D_out, Leaf<G>& leaf) {
+    const uint64_t tkey = p.seed ^ ((uint64_t)ctl.tree_id << 32);
+    typename G::State Sg = Pst;
+    uint32_t Mg = hdr_misc(hdr);
+    const int k0 = (int)hdr_k(hdr);
+    int kg = k0, nexpg = (int)hdr_nexp(hdr);
+    int made = 0, g = 0, spine_lane = -1;
+    // latched per lane while the plan is built
+    typename G::State myP = Pst;
+    uint32_t myPm = Mg;
+    int myk = 0, mynexp = 0, myj = 0, myg = 0, my_parent_lane = -1, my_child_nexp = 0, my_spine_e = -1;
+    bool is_leaf = false, is_self = false, my_path = false;
+    int P_new_nexp = nexpg, P_e = -1, n_self = 0;
+    unsigned long long depth_sum = 0;
+    uint32_t max_depth = 0;
+    for (;;) {
+        if (lane == 0) wp.off[g] = made;
+        if (kg == 0) {                       // move-less node: select() returns it again and again (mcts.cpp:59,138-141)
+            if (lane >= made && lane < B) { is_self = true; myP = Sg; myPm = Mg; myg = g; }
+            n_self = B - made;
+            depth_sum += (unsigned long long)n_self * (unsigned)(d0 + g);
+            max_depth = max(max_depth, (uint32_t)(d0 + g));
+            made = B;
+            break;
+        }
+        const int m = min(kg - nexpg, B - made);
+        if (lane >= made && lane < made + m) {
+            is_leaf = true; myP = Sg; myPm = Mg; myk = kg; mynexp = nexpg; myj = lane - made; myg = g; my_parent_lane = spine_lane;
+        }
+        if (g == 0) P_new_nexp = nexpg + m;
+        else if (lane == spine_lane) my_child_nexp = m;
+        depth_sum += (unsigned long long)m * (unsigned)(d0 + g + 1);
+        max_depth = max(max_depth, (uint32_t)(d0 + g + 1));
+        made += m;
+        if (made >= B) break;
+        // the node is fully expanded and simulations remain: every fresh child has UCT = +inf, the lowest
+        // move index among them wins (mcts.cpp:43,57)
+        int e_star, j_star;
+        lowest_fresh(p.policy, kg, nexpg, m, rng_mix(tkey ^ G::state_key(Sg, Mg)), lane, e_star, j_star);
+        const int next_lane = made - m + j_star;
+        if (g == 0) P_e = e_star;
+        else if (lane == spine_lane) my_spine_e = e_star;
+        if (lane == next_lane) my_path = true;
+        if (lane == 0) wp.pleaf[g] = next_lane;
+        ctl.sum_path_children += (unsigned)kg;
+        uint32_t cm;
+        Sg = G::child(Sg, Mg, nullptr, kg, e_star, cm);
+        Mg = cm;
+        kg = G::count_moves(gx, Sg, Mg);
+        nexpg = 0;
+        spine_lane = next_lane;
+        ++g;
+        if ((uint32_t)(d0 + g) + 2u >= p.path_cap) { ctl.status = -4; return false; }
+    }
+    const int Gc = g + 1;
+    if (lane == 0) wp.off[Gc] = B;
+
+    // ---- all leaves at once
+    int ei = 0, ck = 0;
+    typename G::State cs = myP;
+    uint32_t cmisc = myPm;
+    double val = 0.0;
+    if (is_leaf) {
+        ei = expansion_order(p.policy, myk, mynexp + myj, rng_mix(tkey ^ G::state_key(myP, myPm)));
+        cs = G::child(myP, myPm, nullptr, myk, ei, cmisc);
+        ck = G::count_moves(gx, cs, cmisc);
+        if (kBuiltinEval)
+            val = G::eval_child(cs, cmisc, ck, p.evaluator, rng_mix(tkey ^ G::state_key(cs, cmisc) ^ ((uint64_t)ctl.sims_done << 40) ^ 0x51ull));
+    } else if (is_self) {
+        if (kBuiltinEval)
+            val = G::eval(myP, myPm, p.evaluator, rng_mix(tkey ^ G::state_key(myP, myPm) ^ ((uint64_t)ctl.sims_done << 40) ^ ((uint64_t)lane << 8)));
+    }
+    const int csize = is_leaf ? 1 + G::SS + ck + G::move_slots(ck) : 0;
+    int total;
+    const int off = warp_excl_scan(csize, lane, total);
+    if ((uint64_t)ctl.top + (uint64_t)total > p.arena_slots) { ctl.status = -4; return false; }
+    const uint32_t base = ctl.top;
+    for (int t = lane; t < total; t += 32) arena[base + t] = make_uint4(0, 0, 0, 0);   // edges start at Na=0, Wa=0, no child
+    __syncwarp();
+    const uint32_t my_slot = base + (uint32_t)off;
+    uint32_t pslot = __shfl_sync(FULL_MASK, my_slot, my_parent_lane < 0 ? 0 : my_parent_lane);
+    if (my_parent_lane < 0) pslot = P;
+    leaf.info = 0;
+    leaf.value = val;
+    leaf.st = cs;
+    leaf.misc = cmisc;
+    if (is_leaf) {
+        arena[my_slot] = make_hdr(0, (uint32_t)ck, (uint32_t)my_child_nexp, pslot, (uint32_t)ei, cmisc, (uint32_t)(d0 + myg + 1));
+        G::store_state(arena + my_slot + 1, cs);
+        G::store_moves(gx, arena + my_slot + 1 + G::SS + ck, ck);
+        arena[pslot + 1 + G::SS + ei].w = my_slot;                     // children[move_idx] = child (mcts.cpp:76)
+        leaf.info = (uint32_t)(d0 + myg) | ((uint32_t)ei << LEAF_EDGE_SHIFT) | (my_path ? LEAF_PATH : 0u);
+        if (my_path) path[d0 + myg + 1] = make_uint2(my_slot, my_spine_e >= 0 ? (uint32_t)my_spine_e : 0xFFFFFFFFu);
+    } else if (is_self) {
+        leaf.info = LEAF_SELF | (uint32_t)(d0 + myg);
+        leaf.st = myP;
+        leaf.misc = myPm;
+    }
+    if (lane == 0) {
+        arena[P].y = (uint32_t)k0 | ((uint32_t)P_new_nexp << 16);      // untried.erase (mcts.cpp:72)
+        path[d0] = make_uint2(P, P_e >= 0 ? (uint32_t)P_e : 0xFFFFFFFFu);
+    }
+    ctl.top += (uint32_t)total;
+    ctl.nodes += (uint32_t)(B - n_self);
+    ctl.reevaluated += (uint32_t)n_self;
+    ctl.sum_leaf_depth += depth_sum;
+    ctl.max_leaf_depth = max(ctl.max_leaf_depth, max_depth);
+    __syncwarp();
+    D_out = d0 + Gc - 1;
+    return true;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Chain of expansions, STEPWISE variant (chess): one lane-parallel step per chain level, because the
+// next chain node's move list must exist (a full move generation) before its children can be made.
+// ---------------------------------------------------------------------------------------------
+template <class G, bool kBuiltinEval>
+ZC_D bool expand_stepwise(const SearchParams& p, typename G::Ctx& gx, uint4* __restrict__ arena, uint2* __restrict__ path,
+                          TreeCtl& ctl, int B, int lane, uint32_t P, const uint4& hdr, const typename G::State& st,
+                          int d0, WarpPlan& wp, int& D_out, Leaf<G>& leaf) {
+    const uint64_t tkey = p.seed ^ ((uint64_t)ctl.tree_id << 32);
     int Pk = (int)hdr_k(hdr), Pnexp = (int)hdr_nexp(hdr);
     typename G::State Pst = st;
-    uint32_t Pmisc = misc;
-    int D = depth, made = 0;
+    uint32_t Pmisc = hdr_misc(hdr);
+    int D = d0, made = 0, g = 0;
     leaf.info = 0;
     leaf.value = 0.0;
     leaf.st = st;
-    leaf.misc = misc;
+    leaf.misc = Pmisc;
     while (made < B) {
+        if (lane == 0) wp.off[g] = made;
         if (Pk == 0) {                       // move-less node: select() returns it again and again (:59)
             if (lane >= made && lane < B) {
                 leaf.info = LEAF_SELF | (uint32_t)D;
                 leaf.st = Pst;
                 leaf.misc = Pmisc;
                 if (kBuiltinEval)
-                    leaf.value = G::eval(Pst, Pmisc, p.evaluator, rng_mix(p.seed ^ ((uint64_t)ctl.tree_id << 32) ^ ((uint64_t)ctl.sims_done << 8) ^ (uint64_t)lane));
+                    leaf.value = G::eval(Pst, Pmisc, p.evaluator, rng_mix(tkey ^ G::state_key(Pst, Pmisc) ^ ((uint64_t)ctl.sims_done << 40) ^ ((uint64_t)lane << 8)));
             }
             ctl.reevaluated += (uint32_t)(B - made);
             ctl.sum_leaf_depth += (unsigned long long)(B - made) * (unsigned)D;
@@ -203,11 +351,12 @@ ZC_D bool select_expand(const SearchParams& p, typename G::Ctx& gx, uint4* __res
         const int m = min(Pk - Pnexp, B - made);
         const int j = lane - made;
         const bool act = j >= 0 && j < m;
+        const uint64_t nkey = rng_mix(tkey ^ G::state_key(Pst, Pmisc));
         int ei = 0x7FFFFFFF, ck = 0;
         typename G::State cs = Pst;
         uint32_t cmisc = 0;
         if (act) {
-            ei = expansion_order(p.policy, Pk, Pnexp + j, rng_mix(p.seed ^ ((uint64_t)ctl.tree_id << 32) ^ (uint64_t)P));
+            ei = expansion_order(p.policy, Pk, Pnexp + j, nkey);
             cs = G::child(Pst, Pmisc, arena + P, Pk, ei, cmisc);
             ck = G::count_moves(gx, cs, cmisc);
         }
@@ -229,7 +378,7 @@ ZC_D bool select_expand(const SearchParams& p, typename G::Ctx& gx, uint4* __res
             leaf.st = cs;
             leaf.misc = cmisc;
             if (kBuiltinEval)
-                leaf.value = G::eval_child(cs, cmisc, ck, p.evaluator, rng_mix(p.seed ^ ((uint64_t)ctl.tree_id << 32) ^ ((uint64_t)my_slot << 1) ^ 1ull));
+                leaf.value = G::eval_child(cs, cmisc, ck, p.evaluator, rng_mix(tkey ^ G::state_key(cs, cmisc) ^ ((uint64_t)ctl.sims_done << 40) ^ 0x51ull));
         }
         Pnexp += m;
         if (lane == 0) arena[P].y = (uint32_t)Pk | ((uint32_t)Pnexp << 16);   // untried.erase (:72)
@@ -248,7 +397,10 @@ ZC_D bool select_expand(const SearchParams& p, typename G::Ctx& gx, uint4* __res
         const unsigned who = __ballot_sync(FULL_MASK, act && ei == min_e);
         const int src = __ffs((int)who) - 1;
         if (lane == src) leaf.info |= LEAF_PATH;
-        if (lane == 0) path[D] = make_uint2(P, (uint32_t)min_e);
+        if (lane == 0) {
+            path[D] = make_uint2(P, (uint32_t)min_e);
+            wp.pleaf[g] = src;
+        }
         ctl.sum_path_children += (unsigned)Pk;
         P = __shfl_sync(FULL_MASK, my_slot, src);
         Pst = G::shfl_state(cs, src);
@@ -256,22 +408,37 @@ ZC_D bool select_expand(const SearchParams& p, typename G::Ctx& gx, uint4* __res
         Pk = __shfl_sync(FULL_MASK, ck, src);
         Pnexp = 0;
         ++D;
+        ++g;
         if ((uint32_t)D + 2u >= p.path_cap) { ctl.status = -4; return false; }
     }
-    if (lane == 0) path[D] = make_uint2(P, 0xFFFFFFFFu);
+    if (lane == 0) {
+        path[D] = make_uint2(P, 0xFFFFFFFFu);
+        wp.off[g + 1] = B;
+    }
     __syncwarp();
     D_out = D;
     return true;
 }
 
-// ---------------------------------------------------------------------------------------------
-// backprop of one batch in pending order (mcts.cpp:80-100, 120-124).
-// lane i holds leaf i (info, value); lane l then owns path level l.
-// ---------------------------------------------------------------------------------------------
+// select + expand one batch for one tree.  Leaves end up one per lane (lane i = pending[i]).
+// Returns false if the arena overflowed (tree is then flagged and abandoned).
+template <class G, bool kBuiltinEval>
+ZC_D bool select_expand(const SearchParams& p, typename G::Ctx& gx, uint4* __restrict__ arena, uint2* __restrict__ path,
+                        TreeCtl& ctl, int B, int lane, WarpPlan& wp, int& d0_out, int& D_out, Leaf<G>& leaf) {
+    uint32_t P;
+    int d0;
+    uint4 hdr;
+    typename G::State st;
+    if (!descend<G>(p, arena, path, ctl, lane, P, d0, hdr, st)) return false;
+    d0_out = d0;
+    if (G::kCheapSpine) return expand_spine<G, kBuiltinEval>(p, gx, arena, path, ctl, B, lane, P, hdr, st, d0, wp, D_out, leaf);
+    return expand_stepwise<G, kBuiltinEval>(p, gx, arena, path, ctl, B, lane, P, hdr, st, d0, wp, D_out, leaf);
+}
+
+// leaves that are not on the chain: their node and their edge see exactly one backprop
 template <class G>
-ZC_D void backprop_batch(uint4* __restrict__ arena, const uint2* __restrict__ path, int B, int D, int lane,
-                         uint32_t info, double value) {
-    // leaves that are not on the chain: their node and their edge see exactly one backprop
+ZC_D void backprop_offchain_leaf(uint4* __restrict__ arena, const uint2* __restrict__ path, int B, int lane, uint32_t info,
+                                 double value) {
     if (lane < B && !(info & (LEAF_SELF | LEAF_PATH))) {
         const int li = (int)(info & LEAF_LEVEL_MASK);
         const int e = (int)((info >> LEAF_EDGE_SHIFT) & 0xFFu);
@@ -285,6 +452,17 @@ ZC_D void backprop_batch(uint4* __restrict__ arena, const uint2* __restrict__ pa
         *ep = nv;
         arena[child].x = 1;               // node->N += 1
     }
+}
+
+// ---------------------------------------------------------------------------------------------
+// backprop of one batch in pending order (mcts.cpp:80-100, 120-124).
+// lane i holds leaf i (info, value); lane l then owns path level l and applies the values one by
+// one, in order: the same fp64 operation sequence as the reference, for ANY values (network).
+// ---------------------------------------------------------------------------------------------
+template <class G>
+ZC_D void backprop_batch(uint4* __restrict__ arena, const uint2* __restrict__ path, int B, int D, int lane,
+                         uint32_t info, double value) {
+    backprop_offchain_leaf<G>(arena, path, B, lane, info, value);
     for (int base = 0; base <= D; base += 32) {
         const int l = base + lane;
         const bool on = l <= D;
@@ -328,6 +506,57 @@ ZC_D void backprop_batch(uint4* __restrict__ arena, const uint2* __restrict__ pa
 }
 
 // ---------------------------------------------------------------------------------------------
+// The same backprop in closed form, for evaluators whose values are integers or dyadic rationals
+// (every built-in one): all partial sums are exact in fp64, so the order of the additions cannot
+// change a bit and the 32-step ordered loop collapses into one warp suffix scan.
+//   leaves sorted by level  =>  the leaves below path edge l are a SUFFIX of the pending list
+//   (start = wp.off[g+1], g = l - d0) plus the one leaf that is chain node l+1 (wp.pleaf[g]);
+//   Wa[l] -= (-1)^(l+1) * sum_{i in suffix} (-1)^{depth_i} v_i  +  v_pleaf
+// ---------------------------------------------------------------------------------------------
+template <class G>
+ZC_D void backprop_exact(uint4* __restrict__ arena, const uint2* __restrict__ path, int B, int d0, int D, int lane,
+                         uint32_t info, double value, const WarpPlan& wp) {
+    backprop_offchain_leaf<G>(arena, path, B, lane, info, value);
+    const int li = (int)(info & LEAF_LEVEL_MASK);
+    const int leaf_depth = (info & LEAF_SELF) ? li : li + 1;
+    double S = lane < B ? ((leaf_depth & 1) ? -value : value) : 0.0;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {                       // inclusive suffix sums
+        const double t = __shfl_down_sync(FULL_MASK, S, d);
+        if (lane + d < 32) S += t;
+    }
+    for (int base = 0; base <= D; base += 32) {
+        const int l = base + lane;
+        const bool on = l <= D;
+        const int g = l - d0;
+        int startN = 0, startE = 0, pl = -1;
+        if (on && g >= 0) {
+            startN = wp.off[g];
+            if (l < D) { startE = wp.off[g + 1]; pl = wp.pleaf[g]; }
+        }
+        double suffix = __shfl_sync(FULL_MASK, S, startE & 31);
+        if (startE >= 32) suffix = 0.0;
+        const double vp = __shfl_sync(FULL_MASK, value, pl < 0 ? 0 : pl);
+        if (on) {
+            const uint2 pe = path[l];
+            const uint32_t node = pe.x;
+            arena[node].x += (uint32_t)(B - startN) + (g > 0 ? 1u : 0u);          // node->N
+            if (l < D) {
+                uint4* ep = arena + node + 1 + G::SS + pe.y;
+                uint4 edge = *ep;
+                double W = edge_W(edge);
+                W = W - (((l + 1) & 1) ? -suffix : suffix);
+                if (g >= 0) W = W - vp;
+                edge_set_W(edge, W);
+                edge.z += (uint32_t)(B - startE) + (g >= 0 ? 1u : 0u);            // parent->Na[a]
+                *ep = edge;
+            }
+        }
+    }
+    __syncwarp();
+}
+
+// ---------------------------------------------------------------------------------------------
 // kernels
 // ---------------------------------------------------------------------------------------------
 constexpr int SEARCH_BLOCK = 128;
@@ -336,6 +565,8 @@ constexpr int SEARCH_BLOCK = 128;
 // (mcts.cpp:129-149) for every tree.  Warps pull tree indices from a global counter.
 template <class G>
 __global__ void __launch_bounds__(SEARCH_BLOCK) k_search_fused(SearchParams p) {
+    __shared__ WarpPlan plans[SEARCH_BLOCK / 32];
+    WarpPlan& wp = plans[threadIdx.x >> 5];
     const int lane = threadIdx.x & 31;
     for (;;) {
         int tree = 0;
@@ -348,10 +579,10 @@ __global__ void __launch_bounds__(SEARCH_BLOCK) k_search_fused(SearchParams p) {
         typename G::Ctx gx = G::make_ctx(p, (blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5, lane);
         for (int done = 0; done < p.simulations && ctl.status == 0;) {
             const int B = min(p.batch_size, p.simulations - done);
-            int D;
+            int d0, D;
             Leaf<G> leaf;
-            if (!select_expand<G, true>(p, gx, arena, path, ctl, B, lane, D, leaf)) break;
-            backprop_batch<G>(arena, path, B, D, lane, leaf.info, leaf.value);
+            if (!select_expand<G, true>(p, gx, arena, path, ctl, B, lane, wp, d0, D, leaf)) break;
+            backprop_exact<G>(arena, path, B, d0, D, lane, leaf.info, leaf.value, wp);   // built-in values are exactly summable
             done += B;
             ctl.sims_done += (uint32_t)B;
         }
@@ -362,6 +593,8 @@ __global__ void __launch_bounds__(SEARCH_BLOCK) k_search_fused(SearchParams p) {
 // Split phase 1 (external evaluator): select+expand one batch per tree, pack leaf planes.
 template <class G>
 __global__ void __launch_bounds__(SEARCH_BLOCK) k_select(SearchParams p, int sims_left) {
+    __shared__ WarpPlan plans[SEARCH_BLOCK / 32];
+    WarpPlan& wp = plans[threadIdx.x >> 5];
     const int lane = threadIdx.x & 31;
     const int tree = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
     if (tree >= p.n_trees) return;
@@ -370,12 +603,12 @@ __global__ void __launch_bounds__(SEARCH_BLOCK) k_select(SearchParams p, int sim
     TreeCtl ctl = p.ctl[tree];
     Pending* pd = p.pending + tree;
     const int B = ctl.status == 0 ? min(p.batch_size, sims_left) : 0;
-    int D = 0;
+    int D = 0, d0 = 0;
     Leaf<G> leaf;
     leaf.info = 0;
     bool ok = B > 0;
     typename G::Ctx gx = G::make_ctx(p, (unsigned)tree, lane);
-    if (ok) ok = select_expand<G, false>(p, gx, arena, path, ctl, B, lane, D, leaf);
+    if (ok) ok = select_expand<G, false>(p, gx, arena, path, ctl, B, lane, wp, d0, D, leaf);
     if (lane == 0) {
         pd->B = ok ? B : 0;
         pd->D = D;
