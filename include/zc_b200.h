@@ -163,6 +163,12 @@ int zc_search_results(zc_search *h, zc_root_result *results, int32_t *visits, do
  * oracle/zc_oracle.c:hash_tree): equality means the whole tree matches the reference's bit for bit. */
 int zc_search_tree_hash(zc_search *h, uint64_t *host_hashes, void *stream);
 
+/* Copy the node arena of one tree to the host (16-byte slots; layout in zeroclone_b200/csrc/tree.cuh)
+ * for inspection and invariant checks.  Writes min(used, max_slots) slots, *used = slots in use.
+ * state_slots_out (may be NULL) receives the number of state slots per node (C4 1, chess 2). */
+int zc_search_read_tree(zc_search *h, int tree, void *host_slots, int64_t max_slots, int64_t *used,
+                        int32_t *state_slots_out, void *stream);
+
 /* counters for roofline accounting, summed over trees since the last set_roots */
 typedef struct zc_search_counters {
     int64_t simulations;

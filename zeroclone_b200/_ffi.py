@@ -88,6 +88,7 @@ def lib() -> C.CDLL:
     L.zc_search_results.argtypes = [vp, vp, vp, vp, vp, i32, vp]
     L.zc_search_tree_hash.argtypes = [vp, vp, vp]
     L.zc_search_get_counters.argtypes = [vp, vp, vp]
+    L.zc_search_read_tree.argtypes = [vp, i32, vp, i64, vp, vp, vp]
     for name in ("zc_c4_init_state", "zc_c4_check_win", "zc_c4_check_draw", "zc_chess_init_state", "zc_chess_check_win"):
         getattr(L, name).argtypes = [vp]
     L.zc_c4_legal_moves.argtypes = [vp, vp]

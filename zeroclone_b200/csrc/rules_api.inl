@@ -476,23 +476,29 @@ extern "C" int zc_search_advance(zc_search* h, void* dev_states, const uint8_t* 
     CUDA_TRY(cudaSetDevice(h->device));
     cudaStream_t st = (cudaStream_t)stream;
     const int n = h->n_trees;
-    DevBuf dres, dmv, dkmp;
-    CUDA_TRY(cudaMalloc(&dres.p, sizeof(int32_t) * (size_t)n));
-    CUDA_TRY(cudaMalloc(&dmv.p, sizeof(zc_chess_move) * (size_t)n));
+    if (!h->adv_res_dev) {
+        CUDA_TRY(cudaMalloc((void**)&h->adv_res_dev, sizeof(int32_t) * (size_t)h->max_trees));
+        CUDA_TRY(cudaMalloc((void**)&h->adv_mv_dev, sizeof(zc_chess_move) * (size_t)h->max_trees));
+    }
     if (h->game == ZC_GAME_C4) {
         k_advance_c4<<<(n + 127) / 128, 128, 0, st>>>(h->arena, h->arena_slots, n, (zc_c4_state*)dev_states, dev_active,
-                                                    (int32_t*)dres.p, (zc_chess_move*)dmv.p);
+                                                    h->adv_res_dev, h->adv_mv_dev);
     } else {
         if (!dev_hist || !dev_hist_len || hist_cap < 8) return fail(ZC_EINVAL, "advance: chess needs history buffers");
-        CUDA_TRY(cudaMalloc(&dkmp.p, sizeof(int) * (size_t)n * hist_cap));
+        if (h->adv_kmp_cap < hist_cap) {
+            cudaFree(h->adv_kmp_dev);
+            h->adv_kmp_dev = nullptr;
+            CUDA_TRY(cudaMalloc((void**)&h->adv_kmp_dev, sizeof(int) * (size_t)h->max_trees * hist_cap));
+            h->adv_kmp_cap = hist_cap;
+        }
         k_advance_chess<<<(n + 63) / 64, 64, 0, st>>>(h->arena, h->arena_slots, n, (zc_chess_state*)dev_states, dev_active,
-                                                    dev_hist, dev_hist_len, hist_cap, (int*)dkmp.p, h->scratch,
-                                                    (int32_t*)dres.p, (zc_chess_move*)dmv.p);
+                                                    dev_hist, dev_hist_len, hist_cap, h->adv_kmp_dev, h->scratch,
+                                                    h->adv_res_dev, h->adv_mv_dev);
     }
     h->launches++;
     CUDA_TRY(cudaGetLastError());
-    CUDA_TRY(cudaMemcpyAsync(host_results, dres.p, sizeof(int32_t) * (size_t)n, cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaMemcpyAsync(host_moves, dmv.p, sizeof(zc_chess_move) * (size_t)n, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(host_results, h->adv_res_dev, sizeof(int32_t) * (size_t)n, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(host_moves, h->adv_mv_dev, sizeof(zc_chess_move) * (size_t)n, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
     return ZC_OK;
 }

@@ -56,6 +56,10 @@ struct zc_search {
     zc_chess_move* moves_dev = nullptr;
     int res_stride = 0;
     unsigned long long* hash_dev = nullptr;
+    int32_t* adv_res_dev = nullptr;     // zc_search_advance outputs
+    zc_chess_move* adv_mv_dev = nullptr;
+    int* adv_kmp_dev = nullptr;
+    int adv_kmp_cap = 0;
     int64_t bytes = 0;
     int64_t launches = 0;
     int fused_grid = 0;
@@ -370,6 +374,9 @@ extern "C" int zc_search_destroy(zc_search* h) {
     cudaFree(h->wsum_dev);
     cudaFree(h->moves_dev);
     cudaFree(h->hash_dev);
+    cudaFree(h->adv_res_dev);
+    cudaFree(h->adv_mv_dev);
+    cudaFree(h->adv_kmp_dev);
     delete h;
     return ZC_OK;
 }
@@ -565,6 +572,24 @@ extern "C" int zc_search_tree_hash(zc_search* h, uint64_t* host_hashes, void* st
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaMemcpyAsync(host_hashes, h->hash_dev, sizeof(uint64_t) * h->n_trees, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
+    return ZC_OK;
+}
+
+extern "C" int zc_search_read_tree(zc_search* h, int tree, void* host_slots, int64_t max_slots, int64_t* used,
+                                   int32_t* state_slots_out, void* stream) {
+    if (int rc = check_handle(h)) return rc;
+    if (tree < 0 || tree >= h->n_trees || !host_slots || !used || max_slots < 1) return fail(ZC_EINVAL, "read_tree: bad argument");
+    CUDA_TRY(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    TreeCtl c;
+    CUDA_TRY(cudaMemcpyAsync(&c, h->ctl + tree, sizeof c, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    *used = (int64_t)c.top;
+    const int64_t n = *used < max_slots ? *used : max_slots;
+    CUDA_TRY(cudaMemcpyAsync(host_slots, h->arena + (uint64_t)tree * h->arena_slots, sizeof(uint4) * (size_t)n,
+                             cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    if (state_slots_out) *state_slots_out = h->game == ZC_GAME_C4 ? C4Game::SS : ChessGame::SS;
     return ZC_OK;
 }
 

@@ -16,7 +16,7 @@ from ._ffi import (C4_STATE_DTYPE, CHESS_MOVE_DTYPE, CHESS_STATE_DTYPE, EVAL_C4_
                    EVAL_CHESS_CRUDE, EVAL_EXTERNAL, GAME_C4, GAME_CHESS, POLICY_FIRST, POLICY_LAST, POLICY_RANDOM,
                    ROOT_RESULT_DTYPE, check, lib)
 
-__all__ = ["TreeSearch", "c4_pack_rows", "c4_pack_cols", "c4_unpack_rows"]
+__all__ = ["TreeSearch", "TreeView", "c4_pack_rows", "c4_pack_cols", "c4_unpack_rows"]
 
 
 def _ptr(a: Optional[np.ndarray]):
@@ -126,10 +126,70 @@ class TreeSearch:
         check(lib().zc_search_tree_hash(self._h, _ptr(out), _stream_ptr(stream)))
         return out
 
+    def read_tree(self, tree: int, stream=None) -> "TreeView":
+        """Host copy of one tree's arena as a structured view (inspection / invariant checks)."""
+        cap = 1 << 16
+        while True:
+            buf = np.zeros((cap, 4), dtype=np.uint32)
+            used, ss = C.c_int64(), C.c_int32()
+            check(lib().zc_search_read_tree(self._h, tree, _ptr(buf), cap, C.byref(used), C.byref(ss), _stream_ptr(stream)))
+            if used.value <= cap:
+                return TreeView(buf[:used.value], ss.value, self.game)
+            cap = int(used.value)
+
     def counters(self, stream=None) -> dict:
         c = _ffi.Counters()
         check(lib().zc_search_get_counters(self._h, C.byref(c), _stream_ptr(stream)))
         return {k: int(getattr(c, k)) for k, _ in c._fields_}
+
+
+class TreeView:
+    """Decoded arena of one tree (layout: zeroclone_b200/csrc/tree.cuh)."""
+
+    def __init__(self, slots: np.ndarray, state_slots: int, game: int):
+        self.slots, self.ss, self.game = slots, state_slots, game
+
+    def node(self, slot: int) -> dict:
+        h = self.slots[slot]
+        k, nexp = int(h[1] & 0xFFFF), int(h[1] >> 16)
+        e = self.slots[slot + 1 + self.ss: slot + 1 + self.ss + k]
+        W = (e[:, 0].astype(np.uint64) | (e[:, 1].astype(np.uint64) << np.uint64(32))).view(np.float64) if k else np.zeros(0)
+        return {"slot": slot, "N": int(h[0]), "k": k, "nexp": nexp, "parent": int(h[2]), "parent_edge": int(h[3] & 0xFF),
+                "depth": int(h[3] >> 16), "Na": e[:, 2].astype(np.int64), "Wa": W, "child": e[:, 3].astype(np.int64)}
+
+    def walk(self):
+        """every node, depth-first from the root (slot 0)"""
+        stack = [0]
+        while stack:
+            n = self.node(stack.pop())
+            yield n
+            stack.extend(int(c) for c in n["child"] if c)
+
+    def check_invariants(self, max_abs_value: float) -> int:
+        """Structural invariants of the reference's statistics (mcts.cpp:80-100): returns the node count.
+        - an edge has a child iff it was expanded; #children == n_expanded;
+        - child.N == parent.Na[edge]  (every backprop through the child passes the edge);
+        - non-root N == (evaluations of the node itself) + sum Na, where a node with moves is evaluated
+          exactly once and a move-less node N times;  root N == sum Na;
+        - |Wa| <= Na * max|value|; depth and parent links consistent."""
+        count = 0
+        for n in self.walk():
+            count += 1
+            has = n["child"] != 0
+            assert int(has.sum()) == n["nexp"], (n["slot"], "children vs n_expanded")
+            assert ((n["Na"] > 0) == has).all(), (n["slot"], "visited edge without child or child without visit")
+            assert (np.abs(n["Wa"]) <= n["Na"] * max_abs_value + 1e-9).all(), (n["slot"], "value sum out of range")
+            if n["slot"] == 0:
+                assert n["N"] == int(n["Na"].sum()), "root N"
+            elif n["k"] > 0:
+                assert n["N"] == 1 + int(n["Na"].sum()), (n["slot"], "N != 1 + sum Na")
+            else:
+                assert n["N"] >= 1 and n["nexp"] == 0
+            for e in np.nonzero(has)[0]:
+                c = self.node(int(n["child"][e]))
+                assert c["parent"] == n["slot"] and c["parent_edge"] == int(e) and c["depth"] == n["depth"] + 1
+                assert c["N"] == int(n["Na"][e]), (n["slot"], int(e), "child N != edge Na")
+        return count
 
 
 # ------------------------------------------------------------------------------------ C4 packing
