@@ -2,7 +2,7 @@
 // Semantics (including every deviation from FIDE chess) follow the reference's
 // engine/games/chess/src/chess_backend.cpp, cited per function; the representation does not:
 // the reference scans a 64-byte mailbox, this keeps four bit planes of 4-bit piece codes and
-// derives attack sets with branch-free Kogge-Stone fills, emitting moves in the reference's
+// derives attack sets from per-square ray tables, emitting moves in the reference's
 // scan order (square 0..63, then its per-piece direction order, rays outward) because move
 // order is part of the search result (mcts.cpp:57,154 break ties by index).
 //
@@ -62,55 +62,59 @@ ZC_HD int capture_value(int code) {
     }
 }
 
-// ---- Kogge-Stone occluded fill along one direction.  kLeft: shift toward higher indices.
-template <int kShift, bool kLeft>
-ZC_HD uint64_t shift_dir(uint64_t x) { return kLeft ? (x << kShift) : (x >> kShift); }
-// squares reachable from `from` along the direction until and including the first blocker
-template <int kShift, bool kLeft>
-ZC_HD uint64_t ray(uint64_t from, uint64_t empty, uint64_t wrap) {
-    uint64_t gen = from, pro = empty & wrap;
-    gen |= pro & shift_dir<kShift, kLeft>(gen);
-    pro &= shift_dir<kShift, kLeft>(pro);
-    gen |= pro & shift_dir<2 * kShift, kLeft>(gen);
-    pro &= shift_dir<2 * kShift, kLeft>(pro);
-    gen |= pro & shift_dir<4 * kShift, kLeft>(gen);
-    return shift_dir<kShift, kLeft>(gen) & wrap;
+// ---- per-square masks (tools/gen_chess_tables.py).  Direction ids follow the reference's queen_dirs
+// order (chess_backend.cpp:27-30):  0 (-1,-1)  1 (-1,+1)  2 (+1,-1)  3 (+1,+1)  4 (-1,0)  5 (+1,0)  6 (0,-1)  7 (0,+1)
+#include "chess_tables.inc"
+#ifdef __CUDACC__
+__device__ const uint64_t d_rays[8][64] = ZC_RAY_TABLE;
+__device__ const uint64_t d_knight[64] = ZC_KNIGHT_TABLE;
+__device__ const uint64_t d_king[64] = ZC_KING_TABLE;
+#endif
+static const uint64_t h_rays[8][64] = ZC_RAY_TABLE;
+static const uint64_t h_knight[64] = ZC_KNIGHT_TABLE;
+static const uint64_t h_king[64] = ZC_KING_TABLE;
+
+ZC_HD uint64_t ray_beyond(int d, int sq) {
+#ifdef __CUDA_ARCH__
+    return d_rays[d][sq];
+#else
+    return h_rays[d][sq];
+#endif
 }
-// direction ids in the reference's queen_dirs order (chess_backend.cpp:27-30):
-//   0 (-1,-1)  1 (-1,+1)  2 (+1,-1)  3 (+1,+1)  4 (-1,0)  5 (+1,0)  6 (0,-1)  7 (0,+1)
-ZC_HD uint64_t ray_dir(int d, uint64_t from, uint64_t empty) {
-    switch (d) {
-    case 0: return ray<9, false>(from, empty, ~FILE_H);
-    case 1: return ray<7, false>(from, empty, ~FILE_A);
-    case 2: return ray<7, true>(from, empty, ~FILE_H);
-    case 3: return ray<9, true>(from, empty, ~FILE_A);
-    case 4: return ray<8, false>(from, empty, ~0ull);
-    case 5: return ray<8, true>(from, empty, ~0ull);
-    case 6: return ray<1, false>(from, empty, ~FILE_H);
-    default: return ray<1, true>(from, empty, ~FILE_A);
-    }
+ZC_HD uint64_t knight_targets(int sq) {
+#ifdef __CUDA_ARCH__
+    return d_knight[sq];
+#else
+    return h_knight[sq];
+#endif
 }
+ZC_HD uint64_t king_targets(int sq) {
+#ifdef __CUDA_ARCH__
+    return d_king[sq];
+#else
+    return h_king[sq];
+#endif
+}
+// directions along which the square index grows
 ZC_HD bool dir_ascending(int d) { return d == 2 || d == 3 || d == 5 || d == 7; }
-ZC_HD uint64_t diag_attacks(uint64_t from, uint64_t empty) {
-    return ray<9, false>(from, empty, ~FILE_H) | ray<7, false>(from, empty, ~FILE_A) | ray<7, true>(from, empty, ~FILE_H) |
-           ray<9, true>(from, empty, ~FILE_A);
+// first occupied square of a non-empty subset of a ray, seen from the ray's origin
+ZC_HD int first_on_ray(int d, uint64_t blockers) { return dir_ascending(d) ? zc_ctz64(blockers) : 63 - zc_clz64(blockers); }
+// squares reachable from sq along d, up to and including the first blocker
+ZC_HD uint64_t ray_dir(int d, int sq, uint64_t occ) {
+    uint64_t r = ray_beyond(d, sq);
+    const uint64_t b = r & occ;
+    if (b) r &= ~ray_beyond(d, first_on_ray(d, b));
+    return r;
 }
-ZC_HD uint64_t orth_attacks(uint64_t from, uint64_t empty) {
-    return ray<8, false>(from, empty, ~0ull) | ray<8, true>(from, empty, ~0ull) | ray<1, false>(from, empty, ~FILE_H) |
-           ray<1, true>(from, empty, ~FILE_A);
-}
-ZC_HD uint64_t knight_attacks(uint64_t b) {
-    const uint64_t l1 = (b >> 1) & ~FILE_H, l2 = (b >> 2) & ~(FILE_H | (FILE_H >> 1));
-    const uint64_t r1 = (b << 1) & ~FILE_A, r2 = (b << 2) & ~(FILE_A | (FILE_A << 1));
-    const uint64_t h1 = l1 | r1, h2 = l2 | r2;
-    return (h1 << 16) | (h1 >> 16) | (h2 << 8) | (h2 >> 8);
-}
-ZC_HD uint64_t king_attacks(uint64_t b) {
-    const uint64_t h = ((b >> 1) & ~FILE_H) | ((b << 1) & ~FILE_A), row = h | b;
-    return h | (row << 8) | (row >> 8);
+// is the first piece met from sq along d a member of `attackers` (a subset of occ)?
+ZC_HD bool ray_hits(int d, int sq, uint64_t occ, uint64_t attackers) {
+    const uint64_t r = ray_beyond(d, sq);
+    if (!(r & attackers)) return false;
+    return (attackers >> first_on_ray(d, r & occ)) & 1ull;
 }
 
-// chess_backend.cpp:85-144 -- is the king of `side` on square ksq attacked, given the enemy sets?
+// chess_backend.cpp:85-144 -- is the king of `side` on square ksq attacked, given the enemy sets
+// (all subsets of occ)?
 ZC_HD bool square_attacked(int side, int ksq, uint64_t occ, uint64_t e_pawn, uint64_t e_knight, uint64_t e_diag,
                            uint64_t e_orth, uint64_t e_king) {
     const uint64_t k = bit(ksq);
@@ -118,11 +122,14 @@ ZC_HD bool square_attacked(int side, int ksq, uint64_t occ, uint64_t e_pawn, uin
     const uint64_t pawn_from = side == 0 ? (((k >> 9) & ~FILE_H) | ((k >> 7) & ~FILE_A))
                                          : (((k << 7) & ~FILE_H) | ((k << 9) & ~FILE_A));
     if (pawn_from & e_pawn) return true;
-    if (knight_attacks(k) & e_knight) return true;
-    if (king_attacks(k) & e_king) return true;
-    const uint64_t empty = ~occ;
-    if (e_orth && (orth_attacks(k, empty) & e_orth)) return true;
-    if (e_diag && (diag_attacks(k, empty) & e_diag)) return true;
+    if (knight_targets(ksq) & e_knight) return true;
+    if (king_targets(ksq) & e_king) return true;
+    if (e_diag)
+        for (int d = 0; d < 4; ++d)
+            if (ray_hits(d, ksq, occ, e_diag)) return true;
+    if (e_orth)
+        for (int d = 4; d < 8; ++d)
+            if (ray_hits(d, ksq, occ, e_orth)) return true;
     return false;
 }
 
@@ -209,29 +216,28 @@ ZC_HD int generate(const Board& b, int turn, uint16_t* out) {
                 if (c > 0 && (capturable >> (one - 1) & 1)) out[n++] = pack_move(sq, one - 1);
                 if (c < 7 && (capturable >> (one + 1) & 1)) out[n++] = pack_move(sq, one + 1);
             }
-        } else if (type == KNIGHT || type == KING) {                    // :255-275, :322-340
-            const bool is_king = type == KING;
+        } else if (type == KNIGHT) {                                    // :255-275; knight_dirs order == ascending target
+            uint64_t tg = knight_targets(sq) & targets_ok;
+            while (tg) {
+                const int t = zc_ctz64(tg);
+                tg &= tg - 1;
+                out[n++] = pack_move(sq, t);
+            }
+        } else if (type == KING) {                                      // :322-340, king_dirs order (:31-34)
             for (int d = 0; d < 8; ++d) {
-                int dr, dc;
-                if (is_king) {       // king_dirs (:31-34)
-                    dr = d < 4 ? (d < 2 ? -1 : 1) : (d == 4 ? -1 : d == 5 ? 1 : 0);
-                    dc = d < 4 ? ((d & 1) ? 1 : -1) : (d == 6 ? -1 : d == 7 ? 1 : 0);
-                } else {             // knight_dirs (:17-20)
-                    dr = d < 2 ? -2 : d < 4 ? -1 : d < 6 ? 1 : 2;
-                    dc = (d < 2 || d >= 6) ? ((d & 1) ? 1 : -1) : ((d & 1) ? 2 : -2);
-                }
+                const int dr = d < 4 ? (d < 2 ? -1 : 1) : (d == 4 ? -1 : d == 5 ? 1 : 0);
+                const int dc = d < 4 ? ((d & 1) ? 1 : -1) : (d == 6 ? -1 : d == 7 ? 1 : 0);
                 const int rr = r + dr, cc = c + dc;
                 if (rr < 0 || rr > 7 || cc < 0 || cc > 7) continue;
                 const int t = rr * 8 + cc;
-                if (targets_ok >> t & 1) out[n++] = (uint16_t)(pack_move(sq, t) | (is_king ? MOVE_KING_FLAG : 0));
+                if (targets_ok >> t & 1) out[n++] = (uint16_t)(pack_move(sq, t) | MOVE_KING_FLAG);
             }
         } else if (type == BISHOP || type == ROOK || type == QUEEN) {   // :278-319
             const int d0 = type == ROOK ? 4 : 0, d1 = type == BISHOP ? 4 : 8;
-            const uint64_t me = bit(sq);
             for (int d = d0; d < d1; ++d) {
-                uint64_t tg = ray_dir(d, me, empty) & targets_ok;
+                uint64_t tg = ray_dir(d, sq, s.occ) & targets_ok;
                 const bool asc = dir_ascending(d);
-                while (tg) {                                            // outward = toward/away from index 0
+                while (tg) {                                            // outward from the piece
                     const int t = asc ? zc_ctz64(tg) : 63 - zc_clz64(tg);
                     tg &= ~bit(t);
                     out[n++] = pack_move(sq, t);
