@@ -26,6 +26,9 @@ import sys
 import threading
 import time
 
+# stdout carries exactly one JSON line: NCCL's version banner / debug output goes to stderr
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+
 REPO = os.path.dirname(os.path.abspath(__file__))
 if REPO not in sys.path:
     sys.path.insert(0, REPO)
@@ -186,7 +189,7 @@ def run_ours(args):
             ts.run_network(ev, sims, C_UCT, BATCH, _ffi.POLICY_FIRST)
         else:
             ts.run(sims, C_UCT, BATCH, heur, _ffi.POLICY_FIRST, 0, stream)
-        return ts.results(stats=True, stream=stream)
+        return ts.results(stats=False, stream=stream)    # what get_move returns: the chosen move per tree (mcts.cpp:157-159)
 
     def barrier():
         if world > 1:
