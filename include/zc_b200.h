@@ -236,6 +236,24 @@ int zc_search_advance(zc_search *h, void *dev_states, const uint8_t *dev_active,
 /* state_to_tensor for many packed states at once (host buffers): out[n][C][H][W] float32 */
 int zc_states_to_tensor(int game, const void *states, int n, float *out);
 
+/* ---- value-network evaluator: the whole residual tower as one fused kernel --------------------
+ * Replaces the forward of engine/value_functions.py:78-99 (_batch_worker: model(batch)) over
+ * models/chess_value/network.py:24-45 (stem conv3x3+BN+ReLU, n_blocks residual blocks, average
+ * pool, Linear(128,1), tanh).  BatchNorm (eval mode) must already be folded into conv_w / conv_b.
+ *   conv_w : float32, PyTorch layout [128][Cin][3][3] per convolution, stem first (Cin = 2 for
+ *            Connect Four, 17 for chess), then 2*n_blocks convolutions with Cin = 128
+ *   conv_b : float32 [1 + 2*n_blocks][128]
+ *   head_w : float32 [128], head_b : Linear bias
+ * zc_tower_forward evaluates n_leaves positions packed as bf16 planes [n][Cin][H][W] (the layout
+ * zc_search_select writes with ZC_PLANE_BF16) into dev_values[n] float32, on `stream`, without
+ * synchronising.  Arithmetic: bf16 operands, fp32 accumulation, bf16 activations between layers. */
+typedef struct zc_tower zc_tower;
+int zc_tower_create(int game, int device, int n_blocks, const float *conv_w, const float *conv_b, const float *head_w,
+                    float head_b, zc_tower **out);
+void zc_tower_destroy(zc_tower *t);
+int zc_tower_forward(zc_tower *t, const void *dev_planes_bf16, int n_leaves, float *dev_values, void *stream);
+int64_t zc_tower_launches(const zc_tower *t);
+
 #ifdef __cplusplus
 }
 #endif

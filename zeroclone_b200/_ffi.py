@@ -104,6 +104,12 @@ def lib() -> C.CDLL:
     L.zc_c4_rules_batch.argtypes = [i32, vp, i32, vp, vp]
     L.zc_search_advance.argtypes = [vp, vp, vp, vp, vp, i32, vp, vp, vp]
     L.zc_states_to_tensor.argtypes = [i32, vp, i32, vp]
+    L.zc_tower_create.argtypes = [i32, i32, i32, vp, vp, vp, C.c_float, C.POINTER(vp)]
+    L.zc_tower_destroy.argtypes = [vp]
+    L.zc_tower_destroy.restype = None
+    L.zc_tower_forward.argtypes = [vp, vp, i32, vp, vp]
+    L.zc_tower_launches.argtypes = [vp]
+    L.zc_tower_launches.restype = i64
     assert C.sizeof(RootResult) == ROOT_RESULT_DTYPE.itemsize == 48, (C.sizeof(RootResult), ROOT_RESULT_DTYPE.itemsize)
     assert C.sizeof(C4State) == C4_STATE_DTYPE.itemsize == 24
     assert C.sizeof(ChessState) == CHESS_STATE_DTYPE.itemsize == 72

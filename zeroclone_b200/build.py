@@ -17,7 +17,7 @@ def _newest_source() -> float:
     t = 0.0
     for root in (CSRC, os.path.join(HERE, "..", "include")):
         for f in os.listdir(root):
-            if f.endswith((".cu", ".cuh", ".h", ".inc")):
+            if f.endswith((".cu", ".cuh", ".h", ".inc", ".inl")):
                 t = max(t, os.path.getmtime(os.path.join(root, f)))
     return t
 

@@ -1,0 +1,392 @@
+// Value-network forward (models/chess_value/network.py:24-45 of the reference: stem conv3x3 + BN + ReLU,
+// 8 residual blocks of two conv3x3 + BN, global average pool, Linear(128,1), tanh) as ONE persistent
+// sm_100a kernel.  The reference evaluates leaves through PyTorch (engine/value_functions.py:78-99); here
+// every leaf's activations stay in shared memory for the whole tower and only weights stream in.
+//
+// Mapping
+//   - a tile = NB boards = 128 GEMM rows (Connect Four: 3 boards x 42 cells = 126 rows; chess: 2 x 64);
+//     row p = y*(NB*W) + b*W + x, so a vertical tap is a shift of +-NB*W rows that falls off the tile
+//     into a zero halo, and a horizontal tap is a shift of +-1 row;
+//   - activations live in shared memory K-major WITHOUT swizzle, chunk-major: the 16-byte chunk c
+//     (8 channels) of row r sits at c*A_LBO + r*16.  With SBO = 128 B every row is 16 B after the
+//     previous one, so "the tile shifted by s rows" is the same buffer with the UMMA descriptor's start
+//     address moved by 16*s: the nine taps of a 3x3 convolution are nine descriptors over ONE resident
+//     copy -- no im2col gather, no re-read of activations from L2 (which bounds a generic implicit-GEMM);
+//   - a horizontal shift wraps into the neighbouring board at x = 0 / W-1.  The three tap columns
+//     (dx = -1, 0, +1) therefore accumulate into three TMEM accumulators and the epilogue adds the
+//     dx = -1 (dx = +1) accumulator only to rows with x != 0 (x != W-1);
+//   - tcgen05.mma (cta_group::1, kind::f16, bf16 x bf16 -> fp32, M = N = 128, K = 16) issued by one
+//     thread; per layer and tile 9 taps x 8 k-steps;
+//   - weights: one 32 KB image per (layer, tap) already in the shared-memory layout, fetched with
+//     cp.async.bulk into a ring of stages (mbarrier complete_tx);
+//   - epilogue (8 warps): tcgen05.ld the three accumulators, bias (+ residual, kept in registers as
+//     packed bf16) + ReLU, write the next layer's input in place; two tiles per CTA alternate so the
+//     epilogue of one overlaps the MMAs of the other; accumulators rotate through the 4 x 128 TMEM columns;
+//   - after the last block: per-row dot with the head weights, per-board sum in a fixed order, tanh.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace zc {
+namespace tower {
+
+constexpr int CH = 128;                       // tower width (network.py:26)
+constexpr int KCHUNKS = CH / 8;               // 16-byte chunks per activation row
+constexpr int HALO = 24;                      // zero rows above and below the tile (>= NB*W + 1)
+constexpr int MROWS = 128;                    // UMMA M
+constexpr int BUF_ROWS = HALO + MROWS + HALO;
+constexpr int A_LBO = BUF_ROWS * 16;          // byte distance between k-chunks of the activation buffer
+constexpr int A_BUF_BYTES = KCHUNKS * A_LBO;  // 45056
+constexpr int B_LBO = CH * 16;                // weights: N = 128 rows of 16 B per k-chunk
+constexpr int W_TAP_BYTES = KCHUNKS * B_LBO;  // 32768
+constexpr int NSTAGE = 4;                     // weight ring
+constexpr int NT = 2;                         // tiles in flight per CTA
+constexpr int N_EPI_WARPS = 8;
+constexpr int N_THREADS = (2 + N_EPI_WARPS) * 32;
+constexpr int SMEM_BARS = 0;                  // mbarriers + tmem pointer
+constexpr int SMEM_PART = 256;                // head partial sums [NT][2][128] float
+constexpr int SMEM_ABUF = SMEM_PART + NT * 2 * MROWS * 4;   // 2304
+constexpr int SMEM_WRING = SMEM_ABUF + NT * A_BUF_BYTES;
+constexpr int SMEM_TOTAL = SMEM_WRING + NSTAGE * W_TAP_BYTES;   // 223488
+static_assert(SMEM_ABUF % 16 == 0 && SMEM_WRING % 16 == 0, "descriptor start addresses are in 16-byte units");
+static_assert(SMEM_TOTAL <= 227 * 1024, "shared memory budget");
+
+struct Params {
+    const __nv_bfloat16* planes;   // [n_leaves][CIN][H][W]
+    const uint8_t* wimg;           // [n_layers][9 taps][KCHUNKS][128][8] bf16, taps ordered (dx, dy)
+    const float* bias;             // [n_layers][128] (BatchNorm folded)
+    const float* head_w;           // [128]
+    float head_b;
+    float* out;                    // [n_leaves]
+    int n_leaves;
+    int n_layers;                  // 1 + 2*blocks
+    unsigned int* fault;           // set when a barrier wait times out
+};
+
+// ------------------------------------------------------------------------------------ PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// Bounded wait: a protocol bug must end the kernel with an error, never hang the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, unsigned int* fault, int tag) {
+    uint32_t ok = 0;
+    long long t0 = 0;
+    for (uint32_t it = 0;; ++it) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (ok) return;
+        if ((it & 1023u) == 1023u) {
+            const long long now = clock64();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 4000000000ll) {   // ~2 s
+                atomicExch(fault, 0x80000000u | (unsigned)tag);
+                __threadfence_system();
+                __trap();
+            }
+        }
+    }
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, both K-major
+__device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// UMMA shared-memory descriptor, K-major, SWIZZLE_NONE (cute/arch/mma_sm100_desc.hpp SmemDescriptor):
+// [0,14) start>>4, [16,30) leading byte offset>>4 (between the two k-chunks of one MMA),
+// [32,46) stride byte offset>>4 (between 8-row groups), [46,48) version = 1, [61,64) layout = 0.
+__device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo, uint32_t sbo) {
+    return (uint64_t)((addr >> 4) & 0x3FFFu) | ((uint64_t)((lbo >> 4) & 0x3FFFu) << 16) |
+           ((uint64_t)((sbo >> 4) & 0x3FFFu) << 32) | (1ull << 46);
+}
+// instruction descriptor (InstrDescriptor): c = f32, a = b = bf16, both K-major, N = 128, M = 128
+constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
+
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ float bf16_lo(uint32_t u) { return __uint_as_float(u << 16); }
+__device__ __forceinline__ float bf16_hi(uint32_t u) { return __uint_as_float(u & 0xFFFF0000u); }
+
+template <int H_, int W_, int NB_, int CIN_>
+struct Geom {
+    static constexpr int H = H_, W = W_, NB = NB_, CIN = CIN_;
+    static constexpr int HW = H * W;
+    static constexpr int RS = NB * W;              // rows per board line = vertical shift
+    static constexpr int ROWS = H * RS;            // real rows of a tile
+    static constexpr int CIN16 = (CIN + 15) / 16 * 16;
+    static_assert(ROWS <= MROWS && RS + 1 <= HALO, "tile does not fit");
+};
+using GeomC4 = Geom<6, 7, 3, 2>;      // c4_backend.py:52-61
+using GeomChess = Geom<8, 8, 2, 17>;  // chess_backend.cpp:461-521
+
+// ------------------------------------------------------------------------------------ the kernel
+template <class G>
+__global__ void __launch_bounds__(N_THREADS, 1) k_value_tower(const Params p) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    const uint32_t sbase = smem_u32(smem);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // barriers
+    const uint32_t bar_wfull = sbase + SMEM_BARS, bar_wempty = bar_wfull + 8 * NSTAGE, bar_aready = bar_wempty + 8 * NSTAGE,
+                   bar_accfull = bar_aready + 8 * NT;
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + SMEM_BARS + 8 * (2 * NSTAGE + 2 * NT));
+    float* part = reinterpret_cast<float*>(smem + SMEM_PART);
+
+    // this CTA's share of board groups and the (identical) step sequence every role walks
+    const int n_groups = (p.n_leaves + G::NB - 1) / G::NB;
+    const int cta = blockIdx.x, grid = gridDim.x;
+    const int nj = cta < n_groups ? (n_groups - cta + grid - 1) / grid : 0;
+    const int ns = (nj + NT - 1) / NT;             // groups per tile slot (padded)
+    const int NL = p.n_layers;
+    const int steps_per_slot = ns * NL;
+
+    // zero both activation buffers (halo rows stay zero for the whole kernel)
+    for (int i = threadIdx.x; i < NT * A_BUF_BYTES / 16; i += N_THREADS)
+        reinterpret_cast<uint4*>(smem + SMEM_ABUF)[i] = make_uint4(0, 0, 0, 0);
+    fence_proxy_async();
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < NSTAGE; ++s) {
+            mbar_init(bar_wfull + 8 * s, 1);
+            mbar_init(bar_wempty + 8 * s, 1);
+        }
+        for (int t = 0; t < NT; ++t) {
+            mbar_init(bar_aready + 8 * t, N_EPI_WARPS * 32);
+            mbar_init(bar_accfull + 8 * t, 1);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "r"(512)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_ptr_smem;
+
+    if (warp == 0) {
+        // ============================== weight producer ==============================
+        if (lane == 0) {
+            uint32_t cnt = 0;
+            for (int m = 0; m < steps_per_slot; ++m) {
+                const int layer = m % NL;
+                const uint32_t bytes = layer == 0 ? (G::CIN16 / 8) * B_LBO : W_TAP_BYTES;
+                for (int slot = 0; slot < NT; ++slot)
+                    for (int tap = 0; tap < 9; ++tap, ++cnt) {
+                        const uint32_t st = cnt % NSTAGE, ph = (cnt / NSTAGE) & 1u;
+                        mbar_wait(bar_wempty + 8 * st, ph ^ 1u, p.fault, 1);
+                        mbar_expect_tx(bar_wfull + 8 * st, bytes);
+                        bulk_g2s(sbase + SMEM_WRING + st * W_TAP_BYTES, p.wimg + (size_t)(layer * 9 + tap) * W_TAP_BYTES, bytes,
+                                 bar_wfull + 8 * st);
+                    }
+            }
+        }
+    } else if (warp == 1) {
+        // ============================== MMA issuer ==============================
+        if (lane == 0) {
+            uint32_t wcnt = 0, gcnt = 0;
+            for (int m = 0; m < steps_per_slot; ++m) {
+                const int layer = m % NL;
+                const int ksteps = layer == 0 ? G::CIN16 / 16 : CH / 16;
+                for (int slot = 0; slot < NT; ++slot) {
+                    const int n = m * NT + slot;
+                    mbar_wait(bar_aready + 8 * slot, (uint32_t)m & 1u, p.fault, 2);   // input of this step is in place
+                    tc_fence_after();
+                    const uint32_t abuf = sbase + SMEM_ABUF + slot * A_BUF_BYTES + HALO * 16;
+                    for (int g = 0; g < 3; ++g, ++gcnt) {
+                        if (NT == 2 && g == 1 && n >= 1) {
+                            // accumulators (gcnt % 4) of this and the next group were last used by the previous
+                            // step; its epilogue signals through the a_ready of the step after this one
+                            const int n1 = n + 1;
+                            mbar_wait(bar_aready + 8 * (n1 % NT), (uint32_t)(n1 / NT) & 1u, p.fault, 3);
+                            tc_fence_after();
+                        }
+                        const uint32_t acc = tmem + (gcnt & 3u) * 128u;
+                        for (int dyi = 0; dyi < 3; ++dyi, ++wcnt) {
+                            const uint32_t st = wcnt % NSTAGE, ph = (wcnt / NSTAGE) & 1u;
+                            mbar_wait(bar_wfull + 8 * st, ph, p.fault, 4);
+                            tc_fence_after();
+                            const int shift = (dyi - 1) * G::RS + (g - 1);
+                            const uint32_t a0 = abuf + shift * 16, b0 = sbase + SMEM_WRING + st * W_TAP_BYTES;
+                            for (int k = 0; k < ksteps; ++k)
+                                tc_mma(acc, smem_desc(a0 + 2 * k * A_LBO, A_LBO, 128), smem_desc(b0 + 2 * k * B_LBO, B_LBO, 128),
+                                       IDESC, (dyi | k) != 0);
+                            tc_commit(bar_wempty + 8 * st);   // stage reusable once these MMAs have read it
+                        }
+                    }
+                    tc_commit(bar_accfull + 8 * slot);
+                }
+            }
+        }
+    } else {
+        // ============================== epilogue warps ==============================
+        const int ew = warp - 2;                 // 0..7
+        const int quarter = warp & 3;            // TMEM lane quarter this warp may access
+        const int half = ew >> 2;                // which 64 output channels
+        const int r = quarter * 32 + lane;       // tile row = TMEM lane
+        const bool valid = r < G::ROWS;
+        const int y = r / G::RS, b = (r / G::W) % G::NB, x = r % G::W;
+        const bool use_m = x != 0, use_p = x != G::W - 1;
+        const uint32_t tlane = tmem + ((uint32_t)(quarter * 32) << 16);
+        uint32_t xreg[NT][32];                   // residual stream of this row, packed bf16 (64 channels)
+
+        auto load_planes = [&](int slot, int it) {
+            const int j = it * NT + slot;
+            const long long leaf = (long long)(cta + (long long)j * grid) * G::NB + b;
+            const bool live = valid && j < nj && leaf < p.n_leaves;
+            uint8_t* abuf = smem + SMEM_ABUF + slot * A_BUF_BYTES + (HALO + r) * 16;
+            if (valid) {
+                for (int chunk = half; chunk < G::CIN16 / 8; chunk += 2) {
+                    uint32_t w[4] = {0, 0, 0, 0};
+                    if (live) {
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) {
+                            const int ch = chunk * 8 + e;
+                            if (ch < G::CIN) {
+                                const unsigned short v = reinterpret_cast<const unsigned short*>(
+                                    p.planes)[((size_t)leaf * G::CIN + ch) * G::HW + y * G::W + x];
+                                w[e >> 1] |= (uint32_t)v << ((e & 1) * 16);
+                            }
+                        }
+                    }
+                    *reinterpret_cast<uint4*>(abuf + chunk * A_LBO) = make_uint4(w[0], w[1], w[2], w[3]);
+                }
+            }
+        };
+
+        for (int slot = 0; slot < NT; ++slot) {
+            load_planes(slot, 0);
+            fence_proxy_async();
+            mbar_arrive(bar_aready + 8 * slot);
+        }
+
+        uint32_t gbase = 0;   // first accumulator group of the current step
+        for (int m = 0; m < steps_per_slot; ++m) {
+            const int layer = m % NL, it = m / NL;
+            const bool last = layer == NL - 1;
+            const bool add_res = layer != 0 && (layer & 1) == 0;   // second conv of a block (network.py:20-21)
+            const bool keep = (layer & 1) == 0;                    // output is the next block's input
+            const float* bias = p.bias + layer * CH + half * 64;
+#pragma unroll
+            for (int slot = 0; slot < NT; ++slot, gbase += 3) {
+                mbar_wait(bar_accfull + 8 * slot, (uint32_t)m & 1u, p.fault, 5);
+                tc_fence_after();
+                uint8_t* arow = smem + SMEM_ABUF + slot * A_BUF_BYTES + (HALO + r) * 16;
+                float dot = 0.f;
+#pragma unroll
+                for (int cc = 0; cc < 4; ++cc) {
+                    const uint32_t col = half * 64 + cc * 16;
+                    uint32_t am[16], a0[16], ap[16];
+                    tc_ld16(tlane + ((gbase + 0) & 3u) * 128u + col, am);
+                    tc_ld16(tlane + ((gbase + 1) & 3u) * 128u + col, a0);
+                    tc_ld16(tlane + ((gbase + 2) & 3u) * 128u + col, ap);
+                    tc_wait_ld();
+                    uint32_t o[8];
+#pragma unroll
+                    for (int i = 0; i < 16; i += 2) {
+                        float v0 = __uint_as_float(a0[i]), v1 = __uint_as_float(a0[i + 1]);
+                        if (use_m) { v0 += __uint_as_float(am[i]); v1 += __uint_as_float(am[i + 1]); }
+                        if (use_p) { v0 += __uint_as_float(ap[i]); v1 += __uint_as_float(ap[i + 1]); }
+                        const float2 bb = __ldg(reinterpret_cast<const float2*>(bias + cc * 16 + i));
+                        v0 += bb.x;
+                        v1 += bb.y;
+                        if (add_res) {
+                            const uint32_t xr = xreg[slot][cc * 8 + (i >> 1)];
+                            v0 += bf16_lo(xr);
+                            v1 += bf16_hi(xr);
+                        }
+                        v0 = fmaxf(v0, 0.f);
+                        v1 = fmaxf(v1, 0.f);
+                        const uint32_t pk = pack_bf16(v0, v1);
+                        o[i >> 1] = pk;
+                        if (keep) xreg[slot][cc * 8 + (i >> 1)] = pk;
+                        if (last) {
+                            const float2 hw = __ldg(reinterpret_cast<const float2*>(p.head_w + half * 64 + cc * 16 + i));
+                            dot = fmaf(bf16_lo(pk), hw.x, dot);
+                            dot = fmaf(bf16_hi(pk), hw.y, dot);
+                        }
+                    }
+                    if (valid && !last) {
+                        const int chunk = half * 8 + cc * 2;
+                        *reinterpret_cast<uint4*>(arow + chunk * A_LBO) = make_uint4(o[0], o[1], o[2], o[3]);
+                        *reinterpret_cast<uint4*>(arow + (chunk + 1) * A_LBO) = make_uint4(o[4], o[5], o[6], o[7]);
+                    }
+                }
+                if (last) {
+                    // head: mean over the board's cells, Linear(128,1), tanh (network.py:36-39), fixed summation order
+                    float* pt = part + slot * 2 * MROWS;
+                    pt[half * MROWS + r] = valid ? dot : 0.f;
+                    asm volatile("bar.sync 1, %0;" ::"n"(N_EPI_WARPS * 32) : "memory");
+                    const int et = threadIdx.x - 64;
+                    if (et < G::NB) {
+                        const int j = it * NT + slot;
+                        const long long leaf = (long long)(cta + (long long)j * grid) * G::NB + et;
+                        if (j < nj && leaf < p.n_leaves) {
+                            float s = 0.f;
+                            for (int yy = 0; yy < G::H; ++yy)
+                                for (int xx = 0; xx < G::W; ++xx) {
+                                    const int rr = yy * G::RS + et * G::W + xx;
+                                    s += pt[rr] + pt[MROWS + rr];
+                                }
+                            p.out[leaf] = tanhf(s * (1.0f / G::HW) + p.head_b);
+                        }
+                    }
+                    if (it + 1 < ns) load_planes(slot, it + 1);
+                }
+                fence_proxy_async();
+                tc_fence_before();
+                mbar_arrive(bar_aready + 8 * slot);
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
+    }
+}
+
+}  // namespace tower
+}  // namespace zc

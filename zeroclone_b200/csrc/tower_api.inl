@@ -1,0 +1,126 @@
+// zc_tower_*: the value-network evaluator of the hot path (engine/value_functions.py:61-129 calling
+// models/chess_value/network.py:24-45) as one fused sm_100a kernel.  Included by zc_api.cu.
+#include "tower.cuh"
+
+struct zc_tower {
+    int game = 0, device = 0, n_layers = 0, cin = 0;
+    uint8_t* wimg = nullptr;
+    float* bias = nullptr;
+    float* head_w = nullptr;
+    float head_b = 0.f;
+    unsigned int* fault = nullptr;
+    int n_sms = 0;
+    int64_t launches = 0;
+};
+
+static inline uint16_t f32_to_bf16_rne(float f) {
+    uint32_t u;
+    memcpy(&u, &f, 4);
+    if ((u & 0x7F800000u) == 0x7F800000u) return (uint16_t)((u >> 16) | ((u & 0xFFFFu) ? 0x40u : 0u));
+    u += 0x7FFFu + ((u >> 16) & 1u);
+    return (uint16_t)(u >> 16);
+}
+
+extern "C" int zc_tower_create(int game, int device, int n_blocks, const float* conv_w, const float* conv_b,
+                               const float* head_w, float head_b, zc_tower** out) {
+    if (!out) return fail(ZC_EINVAL, "out is NULL");
+    *out = nullptr;
+    if (game != ZC_GAME_C4 && game != ZC_GAME_CHESS) return fail(ZC_EINVAL, "unknown game");
+    if (n_blocks < 1 || n_blocks > 64 || !conv_w || !conv_b || !head_w) return fail(ZC_EINVAL, "bad tower arguments");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) return fail(ZC_ENODEVICE, "no CUDA device: libzc_b200 has no CPU path");
+    if (device < 0 || device >= ndev) return fail(ZC_EINVAL, "device out of range");
+    CUDA_TRY(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) return fail(ZC_ENODEVICE, "zc_tower needs an sm_100 device (tcgen05/TMEM)");
+
+    using namespace zc::tower;
+    const int cin = game == ZC_GAME_C4 ? GeomC4::CIN : GeomChess::CIN;
+    const int nl = 1 + 2 * n_blocks;
+    // weight images in the shared-memory layout of the B operand: [layer][tap][k-chunk][n][8] bf16,
+    // taps ordered by column offset first (dx = -1, 0, +1), then row offset (dy = -1, 0, +1).
+    // conv_w is PyTorch's [Cout][Cin][kH][kW] per layer, stem first (cross-correlation: dy = kh-1, dx = kw-1).
+    std::vector<uint16_t> img((size_t)nl * 9 * KCHUNKS * CH * 8, 0);
+    size_t woff = 0;
+    for (int l = 0; l < nl; ++l) {
+        const int ci = l == 0 ? cin : CH;
+        for (int g = 0; g < 3; ++g)
+            for (int dyi = 0; dyi < 3; ++dyi) {
+                uint16_t* dst = img.data() + ((size_t)l * 9 + g * 3 + dyi) * KCHUNKS * CH * 8;
+                for (int n = 0; n < CH; ++n)
+                    for (int k = 0; k < ci; ++k)
+                        dst[((size_t)(k / 8) * CH + n) * 8 + (k % 8)] = f32_to_bf16_rne(conv_w[woff + (((size_t)n * ci + k) * 3 + dyi) * 3 + g]);
+            }
+        woff += (size_t)CH * ci * 9;
+    }
+    zc_tower* t = new zc_tower;
+    t->game = game;
+    t->device = device;
+    t->n_layers = nl;
+    t->cin = cin;
+    t->head_b = head_b;
+    t->n_sms = prop.multiProcessorCount;
+    auto cleanup = [&](int rc) {
+        cudaFree(t->wimg); cudaFree(t->bias); cudaFree(t->head_w); cudaFree(t->fault);
+        delete t;
+        return rc;
+    };
+#define TOWER_TRY(expr)                                                                                    \
+    do {                                                                                                   \
+        cudaError_t _e = (expr);                                                                           \
+        if (_e != cudaSuccess) return cleanup(fail(ZC_ECUDA, std::string(#expr) + ": " + cudaGetErrorString(_e))); \
+    } while (0)
+    TOWER_TRY(cudaMalloc(&t->wimg, img.size() * 2));
+    TOWER_TRY(cudaMalloc(&t->bias, sizeof(float) * nl * CH));
+    TOWER_TRY(cudaMalloc(&t->head_w, sizeof(float) * CH));
+    TOWER_TRY(cudaMalloc(&t->fault, sizeof(unsigned int)));
+    TOWER_TRY(cudaMemcpy(t->wimg, img.data(), img.size() * 2, cudaMemcpyHostToDevice));
+    TOWER_TRY(cudaMemcpy(t->bias, conv_b, sizeof(float) * nl * CH, cudaMemcpyHostToDevice));
+    TOWER_TRY(cudaMemcpy(t->head_w, head_w, sizeof(float) * CH, cudaMemcpyHostToDevice));
+    TOWER_TRY(cudaMemset(t->fault, 0, sizeof(unsigned int)));
+    TOWER_TRY(cudaFuncSetAttribute(k_value_tower<GeomC4>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
+    TOWER_TRY(cudaFuncSetAttribute(k_value_tower<GeomChess>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
+#undef TOWER_TRY
+    *out = t;
+    return ZC_OK;
+}
+
+extern "C" void zc_tower_destroy(zc_tower* t) {
+    if (!t) return;
+    cudaSetDevice(t->device);
+    cudaFree(t->wimg);
+    cudaFree(t->bias);
+    cudaFree(t->head_w);
+    cudaFree(t->fault);
+    delete t;
+}
+
+extern "C" int zc_tower_forward(zc_tower* t, const void* dev_planes_bf16, int n_leaves, float* dev_values, void* stream) {
+    if (!t) return fail(ZC_EINVAL, "tower handle is NULL");
+    if (n_leaves < 0 || (n_leaves > 0 && (!dev_planes_bf16 || !dev_values))) return fail(ZC_EINVAL, "bad forward arguments");
+    if (n_leaves == 0) return ZC_OK;
+    using namespace zc::tower;
+    CUDA_TRY(cudaSetDevice(t->device));
+    Params p;
+    p.planes = reinterpret_cast<const __nv_bfloat16*>(dev_planes_bf16);
+    p.wimg = t->wimg;
+    p.bias = t->bias;
+    p.head_w = t->head_w;
+    p.head_b = t->head_b;
+    p.out = dev_values;
+    p.n_leaves = n_leaves;
+    p.n_layers = t->n_layers;
+    p.fault = t->fault;
+    const int nb = t->game == ZC_GAME_C4 ? GeomC4::NB : GeomChess::NB;
+    const int n_groups = (n_leaves + nb - 1) / nb;
+    const int grid = std::max(1, std::min(t->n_sms, (n_groups + NT - 1) / NT));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (t->game == ZC_GAME_C4) k_value_tower<GeomC4><<<grid, N_THREADS, SMEM_TOTAL, st>>>(p);
+    else k_value_tower<GeomChess><<<grid, N_THREADS, SMEM_TOTAL, st>>>(p);
+    CUDA_TRY(cudaGetLastError());
+    ++t->launches;
+    return ZC_OK;
+}
+
+extern "C" int64_t zc_tower_launches(const zc_tower* t) { return t ? t->launches : 0; }

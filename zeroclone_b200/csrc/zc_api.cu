@@ -615,3 +615,4 @@ extern "C" int zc_search_get_counters(zc_search* h, zc_search_counters* out, voi
 }
 
 #include "rules_api.inl"
+#include "tower_api.inl"

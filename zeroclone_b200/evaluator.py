@@ -84,6 +84,85 @@ class NetEvaluator:
         return out
 
 
+class FusedTowerEvaluator:
+    """The same network as ONE hand-written sm_100a kernel (csrc/tower.cuh, zc_tower_* in
+    include/zc_b200.h): activations of a leaf never leave shared memory between the stem and the head.
+    Same call signature as NetEvaluator: evaluator(planes[B,C,H,W] bf16 contiguous, out=float32[B])."""
+
+    dtype = torch.bfloat16
+
+    def __init__(self, model: nn.Module, device="cuda", dtype: torch.dtype = torch.bfloat16):
+        import ctypes as C
+
+        import numpy as np
+
+        from . import _ffi
+
+        if dtype != torch.bfloat16:
+            raise ValueError("the fused tower computes in bf16 (fp32 accumulation)")
+        model = model.eval()
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("FusedTowerEvaluator needs a CUDA device: libzc_b200 has no CPU path")
+        self.in_planes = model.stem[0].in_channels
+        game = {2: _ffi.GAME_C4, 17: _ffi.GAME_CHESS}.get(self.in_planes)
+        if game is None or model.stem[0].out_channels != 128:
+            raise ValueError("fused tower supports the 128-channel tower on Connect Four (2 planes) or chess (17 planes)")
+        ws, bs = [], []
+        w, b = _fold(model.stem[0], model.stem[1])
+        ws.append(w.reshape(-1))
+        bs.append(b)
+        for blk in model.res:
+            for conv, bn in ((blk.seq[0], blk.seq[1]), (blk.seq[3], blk.seq[4])):
+                w, b = _fold(conv, bn)
+                ws.append(w.reshape(-1))
+                bs.append(b)
+        conv_w = np.ascontiguousarray(torch.cat(ws).cpu().numpy(), dtype=np.float32)
+        conv_b = np.ascontiguousarray(torch.cat(bs).cpu().numpy(), dtype=np.float32)
+        lin = model.head[2]
+        head_w = np.ascontiguousarray(lin.weight.detach().float().view(-1).cpu().numpy(), dtype=np.float32)
+        self._h = C.c_void_p()
+        index = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        self._index = index
+        _ffi.check(_ffi.lib().zc_tower_create(game, index, len(model.res), conv_w.ctypes.data_as(C.c_void_p),
+                                              conv_b.ctypes.data_as(C.c_void_p), head_w.ctypes.data_as(C.c_void_p),
+                                              float(lin.bias.detach().float().item()), C.byref(self._h)))
+
+    def close(self) -> None:
+        from . import _ffi
+
+        if getattr(self, "_h", None):
+            _ffi.lib().zc_tower_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def launches(self) -> int:
+        from . import _ffi
+
+        return int(_ffi.lib().zc_tower_launches(self._h))
+
+    def __call__(self, planes: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+        import ctypes as C
+
+        from . import _ffi
+
+        if planes.dtype != torch.bfloat16 or not planes.is_contiguous() or planes.device.type != "cuda":
+            raise ValueError("planes must be a contiguous bf16 CUDA tensor [B, C, H, W]")
+        n = planes.shape[0]
+        if out is None:
+            out = torch.empty(n, dtype=torch.float32, device=planes.device)
+        stream = torch.cuda.current_stream(planes.device).cuda_stream
+        _ffi.check(_ffi.lib().zc_tower_forward(self._h, C.c_void_p(planes.data_ptr()), n, C.c_void_p(out.data_ptr()),
+                                               C.c_void_p(stream)))
+        return out
+
+
 def tower_flops_per_leaf(in_planes: int, h: int, w: int, channels: int = 128, blocks: int = 8) -> float:
     """2*MACs of one forward: stem + 2*blocks convs + head."""
     cells = h * w
