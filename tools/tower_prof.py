@@ -1,0 +1,27 @@
+"""Development aid: run only the fused tower forward a few times (ncu target)."""
+import sys
+import torch
+from zeroclone_b200.evaluator import FusedTowerEvaluator
+
+game = sys.argv[1] if len(sys.argv) > 1 else "c4"
+B = int(sys.argv[2]) if len(sys.argv) > 2 else 131072
+if game == "c4":
+    from zeroclone_b200.models.connect4_value.network import ValueNetwork
+    shape = (2, 6, 7)
+else:
+    from zeroclone_b200.models.chess_value.network import ValueNetwork
+    shape = (17, 8, 8)
+torch.manual_seed(0)
+model = ValueNetwork().eval()
+xd = (torch.rand(B, *shape) < 0.3).to("cuda", torch.bfloat16).contiguous()
+ev = FusedTowerEvaluator(model, "cuda")
+out = torch.empty(B, dtype=torch.float32, device="cuda")
+for _ in range(3):
+    ev(xd, out=out)
+torch.cuda.synchronize()
+a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+a.record()
+ev(xd, out=out)
+b.record()
+torch.cuda.synchronize()
+print(f"{a.elapsed_time(b):.3f} ms", float(out.abs().mean()))

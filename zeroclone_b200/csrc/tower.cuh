@@ -48,7 +48,9 @@ constexpr int SMEM_BARS = 0;                  // mbarriers + tmem pointer
 constexpr int SMEM_PART = 256;                // head partial sums [NT][2][128] float
 constexpr int SMEM_ABUF = SMEM_PART + NT * 2 * MROWS * 4;   // 2304
 constexpr int SMEM_WRING = SMEM_ABUF + NT * A_BUF_BYTES;
-constexpr int SMEM_TOTAL = SMEM_WRING + NSTAGE * W_TAP_BYTES;   // 223488
+constexpr int SMEM_BIAS = SMEM_WRING + NSTAGE * W_TAP_BYTES;    // biases of every layer, fp32
+constexpr int MAX_LAYERS = 17;                                  // network.py:33: stem + 8 blocks
+constexpr int SMEM_TOTAL = SMEM_BIAS + MAX_LAYERS * CH * 4;     // 232192
 static_assert(SMEM_ABUF % 16 == 0 && SMEM_WRING % 16 == 0, "descriptor start addresses are in 16-byte units");
 static_assert(SMEM_TOTAL <= 227 * 1024, "shared memory budget");
 
@@ -182,6 +184,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) k_value_tower(const Params p) {
     // zero both activation buffers (halo rows stay zero for the whole kernel)
     for (int i = threadIdx.x; i < NT * A_BUF_BYTES / 16; i += N_THREADS)
         reinterpret_cast<uint4*>(smem + SMEM_ABUF)[i] = make_uint4(0, 0, 0, 0);
+    for (int i = threadIdx.x; i < NL * CH; i += N_THREADS) reinterpret_cast<float*>(smem + SMEM_BIAS)[i] = p.bias[i];
     fence_proxy_async();
     if (threadIdx.x == 0) {
         for (int s = 0; s < NSTAGE; ++s) {
@@ -266,9 +269,10 @@ __global__ void __launch_bounds__(N_THREADS, 1) k_value_tower(const Params p) {
         const int r = quarter * 32 + lane;       // tile row = TMEM lane
         const bool valid = r < G::ROWS;
         const int y = r / G::RS, b = (r / G::W) % G::NB, x = r % G::W;
-        const bool use_m = x != 0, use_p = x != G::W - 1;
         const uint32_t tlane = tmem + ((uint32_t)(quarter * 32) << 16);
         uint32_t xreg[NT][32];                   // residual stream of this row, packed bf16 (64 channels)
+#pragma unroll
+        for (int i = 0; i < 32; ++i) xreg[0][i] = xreg[1][i] = 0u;
 
         auto load_planes = [&](int slot, int it) {
             const int j = it * NT + slot;
@@ -300,19 +304,19 @@ __global__ void __launch_bounds__(N_THREADS, 1) k_value_tower(const Params p) {
             mbar_arrive(bar_aready + 8 * slot);
         }
 
+        const float fm = x != 0 ? 1.f : 0.f, fp = x != G::W - 1 ? 1.f : 0.f;   // horizontal taps that stay on the board
         uint32_t gbase = 0;   // first accumulator group of the current step
         for (int m = 0; m < steps_per_slot; ++m) {
             const int layer = m % NL, it = m / NL;
             const bool last = layer == NL - 1;
-            const bool add_res = layer != 0 && (layer & 1) == 0;   // second conv of a block (network.py:20-21)
-            const bool keep = (layer & 1) == 0;                    // output is the next block's input
-            const float* bias = p.bias + layer * CH + half * 64;
+            const float fres = (layer != 0 && (layer & 1) == 0) ? 1.f : 0.f;   // second conv of a block adds its input (network.py:20-21)
+            const bool keep = (layer & 1) == 0;                                // output is the next block's input
+            const float4* sb = reinterpret_cast<const float4*>(smem + SMEM_BIAS) + (layer * CH + half * 64) / 4;
 #pragma unroll
             for (int slot = 0; slot < NT; ++slot, gbase += 3) {
                 mbar_wait(bar_accfull + 8 * slot, (uint32_t)m & 1u, p.fault, 5);
                 tc_fence_after();
                 uint8_t* arow = smem + SMEM_ABUF + slot * A_BUF_BYTES + (HALO + r) * 16;
-                float dot = 0.f;
 #pragma unroll
                 for (int cc = 0; cc < 4; ++cc) {
                     const uint32_t col = half * 64 + cc * 16;
@@ -323,27 +327,24 @@ __global__ void __launch_bounds__(N_THREADS, 1) k_value_tower(const Params p) {
                     tc_wait_ld();
                     uint32_t o[8];
 #pragma unroll
-                    for (int i = 0; i < 16; i += 2) {
-                        float v0 = __uint_as_float(a0[i]), v1 = __uint_as_float(a0[i + 1]);
-                        if (use_m) { v0 += __uint_as_float(am[i]); v1 += __uint_as_float(am[i + 1]); }
-                        if (use_p) { v0 += __uint_as_float(ap[i]); v1 += __uint_as_float(ap[i + 1]); }
-                        const float2 bb = __ldg(reinterpret_cast<const float2*>(bias + cc * 16 + i));
-                        v0 += bb.x;
-                        v1 += bb.y;
-                        if (add_res) {
+                    for (int q = 0; q < 4; ++q) {
+                        const float4 bb = sb[cc * 4 + q];
+                        const float bv[4] = {bb.x, bb.y, bb.z, bb.w};
+#pragma unroll
+                        for (int e = 0; e < 4; e += 2) {
+                            const int i = q * 4 + e;
                             const uint32_t xr = xreg[slot][cc * 8 + (i >> 1)];
-                            v0 += bf16_lo(xr);
-                            v1 += bf16_hi(xr);
-                        }
-                        v0 = fmaxf(v0, 0.f);
-                        v1 = fmaxf(v1, 0.f);
-                        const uint32_t pk = pack_bf16(v0, v1);
-                        o[i >> 1] = pk;
-                        if (keep) xreg[slot][cc * 8 + (i >> 1)] = pk;
-                        if (last) {
-                            const float2 hw = __ldg(reinterpret_cast<const float2*>(p.head_w + half * 64 + cc * 16 + i));
-                            dot = fmaf(bf16_lo(pk), hw.x, dot);
-                            dot = fmaf(bf16_hi(pk), hw.y, dot);
+                            float v0 = fmaf(fm, __uint_as_float(am[i]), __uint_as_float(a0[i]));
+                            float v1 = fmaf(fm, __uint_as_float(am[i + 1]), __uint_as_float(a0[i + 1]));
+                            v0 = fmaf(fp, __uint_as_float(ap[i]), v0);
+                            v1 = fmaf(fp, __uint_as_float(ap[i + 1]), v1);
+                            v0 += bv[e];
+                            v1 += bv[e + 1];
+                            v0 = fmaf(fres, bf16_lo(xr), v0);
+                            v1 = fmaf(fres, bf16_hi(xr), v1);
+                            const uint32_t pk = pack_bf16(fmaxf(v0, 0.f), fmaxf(v1, 0.f));
+                            o[i >> 1] = pk;
+                            xreg[slot][cc * 8 + (i >> 1)] = keep ? pk : xr;
                         }
                     }
                     if (valid && !last) {
@@ -353,7 +354,15 @@ __global__ void __launch_bounds__(N_THREADS, 1) k_value_tower(const Params p) {
                     }
                 }
                 if (last) {
-                    // head: mean over the board's cells, Linear(128,1), tanh (network.py:36-39), fixed summation order
+                    // head: mean over the board's cells, Linear(128,1), tanh (network.py:36-39), fixed summation order.
+                    // The last layer closes a block, so xreg holds this row's final activations.
+                    float dot = 0.f;
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        const float2 hw = __ldg(reinterpret_cast<const float2*>(p.head_w + half * 64) + i);
+                        dot = fmaf(bf16_lo(xreg[slot][i]), hw.x, dot);
+                        dot = fmaf(bf16_hi(xreg[slot][i]), hw.y, dot);
+                    }
                     float* pt = part + slot * 2 * MROWS;
                     pt[half * MROWS + r] = valid ? dot : 0.f;
                     asm volatile("bar.sync 1, %0;" ::"n"(N_EPI_WARPS * 32) : "memory");

@@ -26,7 +26,7 @@ extern "C" int zc_tower_create(int game, int device, int n_blocks, const float* 
     if (!out) return fail(ZC_EINVAL, "out is NULL");
     *out = nullptr;
     if (game != ZC_GAME_C4 && game != ZC_GAME_CHESS) return fail(ZC_EINVAL, "unknown game");
-    if (n_blocks < 1 || n_blocks > 64 || !conv_w || !conv_b || !head_w) return fail(ZC_EINVAL, "bad tower arguments");
+    if (n_blocks < 1 || 1 + 2 * n_blocks > zc::tower::MAX_LAYERS || !conv_w || !conv_b || !head_w) return fail(ZC_EINVAL, "bad tower arguments");
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) return fail(ZC_ENODEVICE, "no CUDA device: libzc_b200 has no CPU path");
     if (device < 0 || device >= ndev) return fail(ZC_EINVAL, "device out of range");
