@@ -226,39 +226,52 @@ __global__ void __launch_bounds__(N_THREADS, 1) k_value_tower(const Params p) {
         }
     } else if (warp == 1) {
         // ============================== MMA issuer ==============================
-        if (lane == 0) {
-            uint32_t wcnt = 0, gcnt = 0;
-            for (int m = 0; m < steps_per_slot; ++m) {
-                const int layer = m % NL;
-                const int ksteps = layer == 0 ? G::CIN16 / 16 : CH / 16;
-                for (int slot = 0; slot < NT; ++slot) {
-                    const int n = m * NT + slot;
-                    mbar_wait(bar_aready + 8 * slot, (uint32_t)m & 1u, p.fault, 2);   // input of this step is in place
-                    tc_fence_after();
-                    const uint32_t abuf = sbase + SMEM_ABUF + slot * A_BUF_BYTES + HALO * 16;
-                    for (int g = 0; g < 3; ++g, ++gcnt) {
-                        if (NT == 2 && g == 1 && n >= 1) {
-                            // accumulators (gcnt % 4) of this and the next group were last used by the previous
-                            // step; its epilogue signals through the a_ready of the step after this one
-                            const int n1 = n + 1;
-                            mbar_wait(bar_aready + 8 * (n1 % NT), (uint32_t)(n1 / NT) & 1u, p.fault, 3);
-                            tc_fence_after();
-                        }
-                        const uint32_t acc = tmem + (gcnt & 3u) * 128u;
-                        for (int dyi = 0; dyi < 3; ++dyi, ++wcnt) {
-                            const uint32_t st = wcnt % NSTAGE, ph = (wcnt / NSTAGE) & 1u;
-                            mbar_wait(bar_wfull + 8 * st, ph, p.fault, 4);
-                            tc_fence_after();
-                            const int shift = (dyi - 1) * G::RS + (g - 1);
-                            const uint32_t a0 = abuf + shift * 16, b0 = sbase + SMEM_WRING + st * W_TAP_BYTES;
-                            for (int k = 0; k < ksteps; ++k)
-                                tc_mma(acc, smem_desc(a0 + 2 * k * A_LBO, A_LBO, 128), smem_desc(b0 + 2 * k * B_LBO, B_LBO, 128),
-                                       IDESC, (dyi | k) != 0);
+        // The whole warp walks the loop (warp-uniform control flow keeps descriptors in uniform
+        // registers); one elected lane issues every tcgen05.mma / tcgen05.commit.
+        uint32_t leader;
+        asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(leader));
+        const uint64_t desc_a_hi = smem_desc(0, A_LBO, 128), desc_b_hi = smem_desc(0, B_LBO, 128);
+        uint32_t wcnt = 0, gcnt = 0;
+        for (int m = 0; m < steps_per_slot; ++m) {
+            const int layer = m % NL;
+            const int ksteps = layer == 0 ? G::CIN16 / 16 : CH / 16;
+#pragma unroll 1
+            for (int slot = 0; slot < NT; ++slot) {
+                const int n = m * NT + slot;
+                mbar_wait(bar_aready + 8 * slot, (uint32_t)m & 1u, p.fault, 2);   // input of this step is in place
+                tc_fence_after();
+                const uint32_t abuf = sbase + SMEM_ABUF + slot * A_BUF_BYTES + HALO * 16;
+#pragma unroll 1
+                for (int g = 0; g < 3; ++g, ++gcnt) {
+                    if (NT == 2 && g == 1 && n >= 1) {
+                        // accumulators (gcnt % 4) of this and the next group were last used by the previous
+                        // step; its epilogue signals through the a_ready of the step after this one
+                        const int n1 = n + 1;
+                        mbar_wait(bar_aready + 8 * (n1 % NT), (uint32_t)(n1 / NT) & 1u, p.fault, 3);
+                        tc_fence_after();
+                    }
+                    const uint32_t acc = tmem + (gcnt & 3u) * 128u;
+#pragma unroll 1
+                    for (int dyi = 0; dyi < 3; ++dyi, ++wcnt) {
+                        const uint32_t st = wcnt % NSTAGE, ph = (wcnt / NSTAGE) & 1u;
+                        mbar_wait(bar_wfull + 8 * st, ph, p.fault, 4);
+                        tc_fence_after();
+                        const int shift = (dyi - 1) * G::RS + (g - 1);
+                        const uint64_t ad = desc_a_hi | (uint64_t)(((abuf + shift * 16) >> 4) & 0x3FFFu);
+                        const uint64_t bd = desc_b_hi | (uint64_t)(((sbase + SMEM_WRING + st * W_TAP_BYTES) >> 4) & 0x3FFFu);
+                        if (leader) {
+#pragma unroll
+                            for (int k = 0; k < CH / 16; ++k)
+                                if (k < ksteps)
+                                    tc_mma(acc, ad + (uint64_t)(k * (2 * A_LBO >> 4)), bd + (uint64_t)(k * (2 * B_LBO >> 4)), IDESC,
+                                           (uint32_t)((dyi | k) != 0));
                             tc_commit(bar_wempty + 8 * st);   // stage reusable once these MMAs have read it
                         }
+                        __syncwarp();
                     }
-                    tc_commit(bar_accfull + 8 * slot);
                 }
+                if (leader) tc_commit(bar_accfull + 8 * slot);
+                __syncwarp();
             }
         }
     } else {
