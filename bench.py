@@ -107,6 +107,10 @@ class ClockSampler:
 # ----------------------------------------------------------------------------------------------
 # our arm
 # ----------------------------------------------------------------------------------------------
+# dram__bytes_read.sum + dram__bytes_write.sum per evaluated leaf, from the ncu captures under profiles/
+TOWER_DRAM_BYTES_PER_LEAF = {"connect4": 229.2, "chess": 2400.0}
+
+
 def run_ours(args):
     import numpy as np
     import torch
@@ -143,9 +147,8 @@ def run_ours(args):
             from zeroclone_b200.models.chess_value.network import ValueNetwork
         else:
             from zeroclone_b200.models.connect4_value.network import ValueNetwork
-        torch.backends.cudnn.benchmark = True
         torch.manual_seed(0)
-        ev = NetEvaluator(ValueNetwork().eval(), dev, torch.bfloat16, chunk=131072)
+        ev = NetEvaluator(ValueNetwork().eval(), dev)      # fused sm_100a tower kernel (csrc/tower.cuh)
         flops_leaf = tower_flops_per_leaf(17, 8, 8) if chess else tower_flops_per_leaf(2, 6, 7)
     heur = {"c4_positional": _ffi.EVAL_C4_POSITIONAL, "c4_terminal": _ffi.EVAL_C4_TERMINAL,
             "chess_crude": _ffi.EVAL_CHESS_CRUDE}.get(wl["evaluator"])
@@ -198,7 +201,7 @@ def run_ours(args):
 
     for _ in range(max(args.warmup, 3)):
         search_resident(False)
-    launches0 = ts.counters()["kernel_launches"]
+    launches0 = ts.counters()["kernel_launches"] + (ev.launches if ev is not None else 0)
     sampler = ClockSampler(local)
     barrier()
     sampler.start()
@@ -210,7 +213,7 @@ def run_ours(args):
     barrier()
     clocks = sampler.stop()
     ms = t0.elapsed_time(t1)
-    launches = ts.counters()["kernel_launches"] - launches0
+    launches = ts.counters()["kernel_launches"] + (ev.launches if ev is not None else 0) - launches0
     cnt = ts.counters()
     assert int(res["result"]["root_visits"].min()) == sims, "a tree did not finish its simulations"
 
@@ -261,7 +264,11 @@ def run_ours(args):
         fl = sims_done * flops_leaf * args.steps
         ach = fl / (net_ms * 1e-3) / 1e12
         roofline = {"bound": "tensor", "achieved": ach, "peak": tensor_peak, "unit": "TFLOP/s", "frac": ach / tensor_peak,
-                    "traffic": None, "kernel": "value-net forward (PyTorch/cuDNN bf16), %d forwards" % n_net,
+                    # dram__bytes_read+write of one `ncu --set full` capture of k_value_tower per leaf
+                    # (profiles/r1d_k_value_tower_c4_ncu.txt): planes in, values out, weights from L2
+                    "traffic": TOWER_DRAM_BYTES_PER_LEAF[wl["game"]] * sims_done / (sims // BATCH + (1 if sims % BATCH else 0)),
+                    "traffic_source": "ncu capture of k_value_tower at 131072 leaves, scaled per leaf",
+                    "kernel": "k_value_tower (fused tcgen05 residual tower, bf16 x bf16 -> fp32), %d launches" % n_net,
                     "avg_launch_ms": net_ms / max(1, n_net), "share_of_step": net_ms / ms, "peak_source": peak_src}
     else:
         roofline = dict(roofline_tree, kernel="k_search_fused", peak_source=peak_src)

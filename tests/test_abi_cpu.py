@@ -55,3 +55,18 @@ def test_no_cpu_fallback_without_gpu(L):
     rc = L.zc_search_create(_ffi.GAME_C4, 0, 4, 32, 0, C.byref(h))
     assert rc == _ffi.ZC_ENODEVICE
     assert b"no CPU path" in L.zc_last_error()
+
+
+def test_tower_refuses_without_gpu_and_checks_arguments(L):
+    w = np.zeros(128 * 2 * 9 + 16 * 128 * 128 * 9, dtype=np.float32)
+    b = np.zeros(17 * 128, dtype=np.float32)
+    hw = np.zeros(128, dtype=np.float32)
+    h = C.c_void_p()
+    args = (w.ctypes.data_as(C.c_void_p), b.ctypes.data_as(C.c_void_p), hw.ctypes.data_as(C.c_void_p), C.c_float(0.0), C.byref(h))
+    assert L.zc_tower_create(7, 0, 8, *args) == _ffi.ZC_EINVAL            # unknown game
+    assert L.zc_tower_create(_ffi.GAME_C4, 0, 9, *args) == _ffi.ZC_EINVAL   # deeper than the reference tower
+    if L.zc_device_count() > 0:
+        pytest.skip("a GPU is present")
+    assert L.zc_tower_create(_ffi.GAME_C4, 0, 8, *args) == _ffi.ZC_ENODEVICE
+    assert b"no CPU path" in L.zc_last_error()
+    assert L.zc_tower_forward(None, None, 4, None, None) == _ffi.ZC_EINVAL

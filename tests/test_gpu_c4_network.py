@@ -71,7 +71,7 @@ def test_split_phase_machinery_bit_exact(dtype, sims, batch, policy):
 def test_network_leaf_values_and_root_values_within_tolerance():
     torch.manual_seed(0)
     model = ValueNetwork().eval()
-    ev = NetEvaluator(model, "cuda", torch.bfloat16)
+    ev = NetEvaluator(model, "cuda")
     n, sims = 24, 256
     packed, states = random_roots(n, seed=3)
 

@@ -50,7 +50,7 @@ def test_c4_full_size_value_net_split_phase():
     n, sims = 4096, 800
     torch.manual_seed(0)
     from zeroclone_b200.models.connect4_value.network import ValueNetwork
-    ev = NetEvaluator(ValueNetwork().eval(), "cuda", torch.bfloat16)
+    ev = NetEvaluator(ValueNetwork().eval(), "cuda")
     ts = TreeSearch(_ffi.GAME_C4, n, sims)
     ts.set_roots(c4_roots_set_b(n))
     ts.run_network(ev, sims, 1.4, 32, _ffi.POLICY_FIRST)

@@ -1,0 +1,112 @@
+"""Fused value-tower kernel (csrc/tower.cuh, zc_tower_*) against a plain PyTorch fp32 forward of the
+same network (models/chess_value/network.py:24-45 of the reference).  Tolerance 1e-3 on the tanh
+output, the bound BASELINE.json's north_star states for the neural evaluator (bf16 vs fp32)."""
+import numpy as np
+import pytest
+import torch
+
+from zeroclone_b200.evaluator import NetEvaluator, TorchTowerEvaluator
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-3
+
+
+def make_model(game, perturb_bn, seed=0):
+    if game == "c4":
+        from zeroclone_b200.models.connect4_value.network import ValueNetwork
+        shape = (2, 6, 7)
+    else:
+        from zeroclone_b200.models.chess_value.network import ValueNetwork
+        shape = (17, 8, 8)
+    torch.manual_seed(seed)
+    model = ValueNetwork().eval()
+    if perturb_bn:   # running statistics and affine terms away from their defaults so the fold is exercised
+        for m in model.modules():
+            if isinstance(m, torch.nn.BatchNorm2d):
+                m.running_mean.normal_(0, 0.1)
+                m.running_var.uniform_(0.5, 1.5)
+                m.weight.data.uniform_(0.8, 1.2)
+                m.bias.data.normal_(0, 0.1)
+    return model, shape
+
+
+def random_planes(n, shape, seed):
+    g = torch.Generator().manual_seed(seed)
+    x = (torch.rand(n, *shape, generator=g) < 0.3).float()
+    if shape[0] == 2:
+        x[:, 1] *= 1 - x[:, 0]      # a cell holds one disc
+    return x
+
+
+@pytest.mark.parametrize("game", ["c4", "chess"])
+@pytest.mark.parametrize("perturb_bn", [False, True])
+def test_tower_matches_fp32_reference(game, perturb_bn):
+    model, shape = make_model(game, perturb_bn)
+    n = 3000
+    x = random_planes(n, shape, 1)
+    with torch.no_grad():
+        ref = model(x).view(-1)
+    ev = NetEvaluator(model, "cuda")
+    got = ev(x.to("cuda", torch.bfloat16)).cpu()
+    err = (got - ref).abs().max().item()
+    assert err < TOL, f"|fused bf16 - fp32| max {err}"
+    assert ev.launches == 1
+
+
+@pytest.mark.parametrize("game", ["c4", "chess"])
+def test_tower_ragged_batches_and_determinism(game):
+    """every leaf is evaluated independently of its neighbours in the tile and of the batch size:
+    the same position must give the same bits at any offset, for any n (incl. n not a multiple of the
+    boards per tile, n smaller than one tile, n = 0)"""
+    model, shape = make_model(game, True, seed=3)
+    x = random_planes(1500, shape, 2).to("cuda", torch.bfloat16)
+    ev = NetEvaluator(model, "cuda")
+    full = ev(x).cpu()
+    again = ev(x).cpu()
+    assert torch.equal(full, again), "not deterministic"
+    assert ev(x[:0]).numel() == 0
+    for n in (1, 2, 3, 4, 5, 7, 127, 128, 129, 887):
+        part = ev(x[:n].contiguous()).cpu()
+        assert torch.equal(part, full[:n]), n
+    off = ev(x[301:1207].contiguous()).cpu()
+    assert torch.equal(off, full[301:1207])
+    # a leaf does not see its tile neighbours: same leaf surrounded by different boards
+    y = x.clone()
+    y[1::2] = 0
+    alt = ev(y).cpu()
+    assert torch.equal(alt[0::2], full[0::2])
+
+
+@pytest.mark.parametrize("game", ["c4", "chess"])
+def test_tower_agrees_with_torch_bf16_path(game):
+    model, shape = make_model(game, False)
+    x = random_planes(2048, shape, 5).to("cuda", torch.bfloat16)
+    a = NetEvaluator(model, "cuda")(x).cpu()
+    b = TorchTowerEvaluator(model, "cuda", torch.bfloat16)(x).cpu()
+    assert (a - b).abs().max().item() < 2 * TOL
+
+
+def test_tower_full_batch_size():
+    """131072 leaves = one search batch of BASELINE configs[1] (4096 trees x 32): spot-check against fp32"""
+    model, shape = make_model("c4", False)
+    n = 131072
+    x = random_planes(n, shape, 7)
+    ev = NetEvaluator(model, "cuda")
+    got = ev(x.to("cuda", torch.bfloat16)).cpu()
+    idx = torch.randint(0, n, (2048,), generator=torch.Generator().manual_seed(0))
+    idx[-1] = n - 1
+    with torch.no_grad():
+        ref = model(x[idx]).view(-1)
+    assert (got[idx] - ref).abs().max().item() < TOL
+    assert torch.isfinite(got).all()
+
+
+def test_tower_rejects_what_it_cannot_compute():
+    model, shape = make_model("c4", False)
+    ev = NetEvaluator(model, "cuda")
+    with pytest.raises(ValueError):
+        ev(torch.zeros(4, *shape, device="cuda", dtype=torch.float32))
+    with pytest.raises(ValueError):
+        ev(torch.zeros(4, *shape, dtype=torch.bfloat16))
+    with pytest.raises(ValueError):
+        NetEvaluator(model, "cuda", torch.float16)

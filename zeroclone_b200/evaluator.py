@@ -3,9 +3,11 @@ reference's Value class (engine/value_functions.py:61-129) without the worker th
 per-state queues -- every tree's pending leaves are already one contiguous device batch, so the
 evaluation is ONE forward per search batch.
 
-The forward is PyTorch (cuDNN/cuBLAS tensor-core kernels): it is the one dense contraction of
-the path.  BatchNorm (eval mode, network.py:15,18,30) is folded into the convolution weights in
-fp32 before the cast to the compute dtype.
+`NetEvaluator` (= FusedTowerEvaluator) is the product path: the whole tower as one hand-written
+sm_100a kernel (csrc/tower.cuh) behind the C-ABI (zc_tower_*).  `TorchTowerEvaluator` is the same
+network through PyTorch/cuDNN; it exists for A/B timing, for tests, and for the fp16 / fp32 plane
+dtypes the kernel does not compute in.  BatchNorm (eval mode, network.py:15,18,30) is folded into
+the convolution weights in fp32 before the cast to the compute dtype in both.
 """
 from __future__ import annotations
 
@@ -25,8 +27,8 @@ def _fold(conv: nn.Conv2d, bn: nn.BatchNorm2d) -> Tuple[torch.Tensor, torch.Tens
     return w * scale.view(-1, 1, 1, 1), b
 
 
-class NetEvaluator:
-    """values = tanh(head(res(stem(planes))))  for planes[B, C, H, W] in `dtype`; returns float32[B]."""
+class TorchTowerEvaluator:
+    """PyTorch/cuDNN reference of the fused kernel.  values = tanh(head(res(stem(planes))))  for planes[B, C, H, W] in `dtype`; returns float32[B]."""
 
     def __init__(self, model: nn.Module, device="cuda", dtype: torch.dtype = torch.bfloat16, chunk: int = 131072):
         model = model.eval()
@@ -87,7 +89,7 @@ class NetEvaluator:
 class FusedTowerEvaluator:
     """The same network as ONE hand-written sm_100a kernel (csrc/tower.cuh, zc_tower_* in
     include/zc_b200.h): activations of a leaf never leave shared memory between the stem and the head.
-    Same call signature as NetEvaluator: evaluator(planes[B,C,H,W] bf16 contiguous, out=float32[B])."""
+    Call: evaluator(planes[B,C,H,W] bf16 contiguous, out=float32[B])."""
 
     dtype = torch.bfloat16
 
@@ -161,6 +163,9 @@ class FusedTowerEvaluator:
         _ffi.check(_ffi.lib().zc_tower_forward(self._h, C.c_void_p(planes.data_ptr()), n, C.c_void_p(out.data_ptr()),
                                                C.c_void_p(stream)))
         return out
+
+
+NetEvaluator = FusedTowerEvaluator
 
 
 def tower_flops_per_leaf(in_planes: int, h: int, w: int, channels: int = 128, blocks: int = 8) -> float:

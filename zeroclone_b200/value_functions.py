@@ -2,7 +2,7 @@
 `value(state, **kw)`, `value.batch(states, backend=)` -- plus `device_spec()`, which tells the
 batched CUDA search how to evaluate leaves for this Value:
    ("builtin", ZC_EVAL_*)   heuristic computed inside the search kernel, or
-   ("network", NetEvaluator) one batched bf16 forward per search batch.
+   ("network", NetEvaluator) one batched bf16 forward per search batch (fused tower kernel).
 
 Names: random_rollout, crude_chess_score, network_latest, network_at_path (the reference's,
 value_functions.py:35-129) and c4_terminal / c4_positional (deterministic parity evaluators,
@@ -65,12 +65,14 @@ class Value:
     def evaluator(self):
         if self._net is None:
             import torch
-            from .evaluator import NetEvaluator
+            from .evaluator import NetEvaluator, TorchTowerEvaluator
             if not torch.cuda.is_available():
                 raise RuntimeError("the neural evaluator runs on the GPU only (no CPU fallback)")
             dtype = {"bf16": torch.bfloat16, "fp16": torch.float16, "fp32": torch.float32}[self.init_args.get("dtype", "bf16")]
             dev = torch.device("cuda", self.init_args.get("device", torch.cuda.current_device()))
-            self._net = NetEvaluator(self.model, dev, dtype)
+            # bf16 (the default) is the fused sm_100a tower kernel; fp16 / fp32 are explicit requests for the
+            # PyTorch reference forward
+            self._net = NetEvaluator(self.model, dev) if dtype == torch.bfloat16 else TorchTowerEvaluator(self.model, dev, dtype)
         return self._net
 
     # ------------------------------------------------------------------ heuristics (host, per state)
