@@ -16,12 +16,14 @@ model = ValueNetwork().eval()
 xd = (torch.rand(B, *shape) < 0.3).to("cuda", torch.bfloat16).contiguous()
 ev = FusedTowerEvaluator(model, "cuda")
 out = torch.empty(B, dtype=torch.float32, device="cuda")
-for _ in range(3):
+reps = int(sys.argv[3]) if len(sys.argv) > 3 else 1
+for _ in range(3 if reps == 1 else 20):
     ev(xd, out=out)
 torch.cuda.synchronize()
 a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 a.record()
-ev(xd, out=out)
+for _ in range(reps):
+    ev(xd, out=out)
 b.record()
 torch.cuda.synchronize()
-print(f"{a.elapsed_time(b):.3f} ms", float(out.abs().mean()))
+print(f"{a.elapsed_time(b) / reps:.3f} ms", float(out.abs().mean()))

@@ -40,7 +40,7 @@ constexpr int A_LBO = BUF_ROWS * 16;          // byte distance between k-chunks 
 constexpr int A_BUF_BYTES = KCHUNKS * A_LBO;  // 45056
 constexpr int B_LBO = CH * 16;                // weights: N = 128 rows of 16 B per k-chunk
 constexpr int W_TAP_BYTES = KCHUNKS * B_LBO;  // 32768
-constexpr int NSTAGE = 4;                     // weight ring
+constexpr int RING_BYTES = 4 * W_TAP_BYTES;    // weight ring: 4 stages of a whole tap, or 8 of the half a paired CTA holds
 constexpr int NT = 2;                         // tiles in flight per CTA
 constexpr int N_EPI_WARPS = 8;
 constexpr int N_THREADS = (2 + N_EPI_WARPS) * 32;
@@ -48,7 +48,7 @@ constexpr int SMEM_BARS = 0;                  // mbarriers + tmem pointer
 constexpr int SMEM_PART = 256;                // head partial sums [NT][2][128] float
 constexpr int SMEM_ABUF = SMEM_PART + NT * 2 * MROWS * 4;   // 2304
 constexpr int SMEM_WRING = SMEM_ABUF + NT * A_BUF_BYTES;
-constexpr int SMEM_BIAS = SMEM_WRING + NSTAGE * W_TAP_BYTES;    // biases of every layer, fp32
+constexpr int SMEM_BIAS = SMEM_WRING + RING_BYTES;    // biases of every layer, fp32
 constexpr int MAX_LAYERS = 17;                                  // network.py:33: stem + 8 blocks
 constexpr int SMEM_TOTAL = SMEM_BIAS + MAX_LAYERS * CH * 4;     // 232192
 static_assert(SMEM_ABUF % 16 == 0 && SMEM_WRING % 16 == 0, "descriptor start addresses are in 16-byte units");
@@ -57,6 +57,7 @@ static_assert(SMEM_TOTAL <= 227 * 1024, "shared memory budget");
 struct Params {
     const __nv_bfloat16* planes;   // [n_leaves][CIN][H][W]
     const uint8_t* wimg;           // [n_layers][9 taps][KCHUNKS][128][8] bf16, taps ordered (dx, dy)
+    const uint8_t* wimg2;          // [n_layers][9 taps][2 halves of N][KCHUNKS][64][8]: what each CTA of a pair holds
     const float* bias;             // [n_layers][128] (BatchNorm folded)
     const float* head_w;           // [128]
     float head_b;
@@ -64,6 +65,7 @@ struct Params {
     int n_leaves;
     int n_layers;                  // 1 + 2*blocks
     unsigned int* fault;           // set when a barrier wait times out
+    int dbg;                       // timing experiments only (ZC_TOWER_DEBUG): results are wrong when non-zero
 };
 
 // ------------------------------------------------------------------------------------ PTX helpers
@@ -107,6 +109,39 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
                  "l"(src), "r"(bytes), "r"(bar)
                  : "memory");
 }
+// cta_group::2: one instruction drives the tensor cores of both CTAs of a pair (M = 256: each CTA its own
+// 128 rows of A from its own shared memory at the descriptor's offset, and half of B's N rows)
+__device__ __forceinline__ void tc_mma2(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// arrives on the barrier at this offset in both CTAs of the pair once the MMAs issued so far are complete
+__device__ __forceinline__ void tc_commit2(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+                 "h"((uint16_t)3)
+                 : "memory");
+}
+// address of the same shared-memory offset in CTA `rank` of the cluster, and an arrive on a barrier there
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void cluster_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -141,6 +176,7 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo, uint3
 }
 // instruction descriptor (InstrDescriptor): c = f32, a = b = bf16, both K-major, N = 128, M = 128
 constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
+constexpr uint32_t IDESC2 = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) << 17) | ((256u >> 4) << 24);   // M = 256 over the pair
 
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
     __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
@@ -162,22 +198,28 @@ using GeomC4 = Geom<6, 7, 3, 2>;      // c4_backend.py:52-61
 using GeomChess = Geom<8, 8, 2, 17>;  // chess_backend.cpp:461-521
 
 // ------------------------------------------------------------------------------------ the kernel
-template <class G>
+template <class G, bool PAIR>
 __global__ void __launch_bounds__(N_THREADS, 1) k_value_tower(const Params p) {
     extern __shared__ __align__(128) uint8_t smem[];
     const uint32_t sbase = smem_u32(smem);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // barriers
+    constexpr int NSTAGE = PAIR ? 8 : 4;
+    constexpr uint32_t STAGE_BYTES = RING_BYTES / NSTAGE;        // a whole tap image, or this CTA's half of it
+    constexpr uint32_t BLBO = PAIR ? B_LBO / 2 : B_LBO;          // k-chunk stride of the B operand held here
     const uint32_t bar_wfull = sbase + SMEM_BARS, bar_wempty = bar_wfull + 8 * NSTAGE, bar_aready = bar_wempty + 8 * NSTAGE,
-                   bar_accfull = bar_aready + 8 * NT;
-    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + SMEM_BARS + 8 * (2 * NSTAGE + 2 * NT));
+                   bar_accfull = bar_aready + 8 * NT, bar_wpeer = bar_accfull + 8 * NT;
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + SMEM_BARS + 8 * (3 * NSTAGE + 2 * NT));
+    static_assert(8 * (3 * 8 + 2 * NT) + 4 <= SMEM_PART, "barrier area");
     float* part = reinterpret_cast<float*>(smem + SMEM_PART);
 
     // this CTA's share of board groups and the (identical) step sequence every role walks
     const int n_groups = (p.n_leaves + G::NB - 1) / G::NB;
     const int cta = blockIdx.x, grid = gridDim.x;
     const int nj = cta < n_groups ? (n_groups - cta + grid - 1) / grid : 0;
-    const int ns = (nj + NT - 1) / NT;             // groups per tile slot (padded)
+    // groups per tile slot, padded to the longest CTA: the CTAs of a cluster share one weight stream
+    const int ns = ((n_groups + grid - 1) / grid + NT - 1) / NT;
+    const uint32_t crank = PAIR ? cluster_ctarank() : 0u;   // 0 issues the pair's MMAs
     const int NL = p.n_layers;
     const int steps_per_slot = ns * NL;
 
@@ -190,20 +232,28 @@ __global__ void __launch_bounds__(N_THREADS, 1) k_value_tower(const Params p) {
         for (int s = 0; s < NSTAGE; ++s) {
             mbar_init(bar_wfull + 8 * s, 1);
             mbar_init(bar_wempty + 8 * s, 1);
+            mbar_init(bar_wpeer + 8 * s, 1);      // pair: the other CTA's half of a stage has landed
         }
         for (int t = 0; t < NT; ++t) {
-            mbar_init(bar_aready + 8 * t, N_EPI_WARPS * 32);
+            mbar_init(bar_aready + 8 * t, (PAIR ? 2 : 1) * N_EPI_WARPS);   // one arrival per epilogue warp; pair: both CTAs report to rank 0
             mbar_init(bar_accfull + 8 * t, 1);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "r"(512)
-                     : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if (PAIR) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "r"(512)
+                         : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "r"(512)
+                         : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     tc_fence_before();
     __syncthreads();
+    if (PAIR) cluster_sync();   // the peer's barriers and zeroed buffers exist before anything touches them
     tc_fence_after();
     const uint32_t tmem = *tmem_ptr_smem;
 
@@ -213,14 +263,16 @@ __global__ void __launch_bounds__(N_THREADS, 1) k_value_tower(const Params p) {
             uint32_t cnt = 0;
             for (int m = 0; m < steps_per_slot; ++m) {
                 const int layer = m % NL;
-                const uint32_t bytes = layer == 0 ? (G::CIN16 / 8) * B_LBO : W_TAP_BYTES;
+                const uint32_t bytes = layer == 0 ? (G::CIN16 / 8) * BLBO : STAGE_BYTES;
                 for (int slot = 0; slot < NT; ++slot)
                     for (int tap = 0; tap < 9; ++tap, ++cnt) {
                         const uint32_t st = cnt % NSTAGE, ph = (cnt / NSTAGE) & 1u;
                         mbar_wait(bar_wempty + 8 * st, ph ^ 1u, p.fault, 1);
+                        if ((p.dbg & 4) && cnt >= NSTAGE) { mbar_arrive(bar_wfull + 8 * st); continue; }
                         mbar_expect_tx(bar_wfull + 8 * st, bytes);
-                        bulk_g2s(sbase + SMEM_WRING + st * W_TAP_BYTES, p.wimg + (size_t)(layer * 9 + tap) * W_TAP_BYTES, bytes,
-                                 bar_wfull + 8 * st);
+                        const uint8_t* src = PAIR ? p.wimg2 + ((size_t)(layer * 9 + tap) * 2 + crank) * STAGE_BYTES
+                                                  : p.wimg + (size_t)(layer * 9 + tap) * STAGE_BYTES;
+                        bulk_g2s(sbase + SMEM_WRING + st * STAGE_BYTES, src, bytes, bar_wfull + 8 * st);
                     }
             }
         }
@@ -230,8 +282,18 @@ __global__ void __launch_bounds__(N_THREADS, 1) k_value_tower(const Params p) {
         // registers); one elected lane issues every tcgen05.mma / tcgen05.commit.
         uint32_t leader;
         asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(leader));
-        const uint64_t desc_a_hi = smem_desc(0, A_LBO, 128), desc_b_hi = smem_desc(0, B_LBO, 128);
+        const uint64_t desc_a_hi = smem_desc(0, A_LBO, 128), desc_b_hi = smem_desc(0, BLBO, 128);
         uint32_t wcnt = 0, gcnt = 0;
+        if (PAIR && crank != 0) {
+            // the pair's second CTA issues nothing; it tells rank 0 when its half of each weight stage has landed
+            const uint32_t total = (uint32_t)steps_per_slot * NT * 9u;
+            for (; wcnt < total; ++wcnt) {
+                const uint32_t st = wcnt % NSTAGE, ph = (wcnt / NSTAGE) & 1u;
+                mbar_wait(bar_wfull + 8 * st, ph, p.fault, 6);
+                if (leader) mbar_arrive_cluster(map_to_cta(bar_wpeer + 8 * st, 0));
+                __syncwarp();
+            }
+        } else
         for (int m = 0; m < steps_per_slot; ++m) {
             const int layer = m % NL;
             const int ksteps = layer == 0 ? G::CIN16 / 16 : CH / 16;
@@ -243,7 +305,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) k_value_tower(const Params p) {
                 const uint32_t abuf = sbase + SMEM_ABUF + slot * A_BUF_BYTES + HALO * 16;
 #pragma unroll 1
                 for (int g = 0; g < 3; ++g, ++gcnt) {
-                    if (NT == 2 && g == 1 && n >= 1) {
+                    if (NT == 2 && g == 1 && n >= 1 && !(p.dbg & 1)) {
                         // accumulators (gcnt % 4) of this and the next group were last used by the previous
                         // step; its epilogue signals through the a_ready of the step after this one
                         const int n1 = n + 1;
@@ -255,22 +317,33 @@ __global__ void __launch_bounds__(N_THREADS, 1) k_value_tower(const Params p) {
                     for (int dyi = 0; dyi < 3; ++dyi, ++wcnt) {
                         const uint32_t st = wcnt % NSTAGE, ph = (wcnt / NSTAGE) & 1u;
                         mbar_wait(bar_wfull + 8 * st, ph, p.fault, 4);
+                        if (PAIR) mbar_wait(bar_wpeer + 8 * st, ph, p.fault, 7);
                         tc_fence_after();
                         const int shift = (dyi - 1) * G::RS + (g - 1);
                         const uint64_t ad = desc_a_hi | (uint64_t)(((abuf + shift * 16) >> 4) & 0x3FFFu);
-                        const uint64_t bd = desc_b_hi | (uint64_t)(((sbase + SMEM_WRING + st * W_TAP_BYTES) >> 4) & 0x3FFFu);
+                        const uint64_t bd = desc_b_hi | (uint64_t)(((sbase + SMEM_WRING + st * STAGE_BYTES) >> 4) & 0x3FFFu);
                         if (leader) {
 #pragma unroll
                             for (int k = 0; k < CH / 16; ++k)
-                                if (k < ksteps)
-                                    tc_mma(acc, ad + (uint64_t)(k * (2 * A_LBO >> 4)), bd + (uint64_t)(k * (2 * B_LBO >> 4)), IDESC,
-                                           (uint32_t)((dyi | k) != 0));
-                            tc_commit(bar_wempty + 8 * st);   // stage reusable once these MMAs have read it
+                                if (k < ksteps) {
+                                    if (PAIR)
+                                        tc_mma2(acc, ad + (uint64_t)(k * (2 * A_LBO >> 4)), bd + (uint64_t)(k * (2 * BLBO >> 4)), IDESC2,
+                                                (uint32_t)((dyi | k) != 0));
+                                    else
+                                        tc_mma(acc, ad + (uint64_t)(k * (2 * A_LBO >> 4)), bd + (uint64_t)(k * (2 * BLBO >> 4)), IDESC,
+                                               (uint32_t)((dyi | k) != 0));
+                                }
+                            // stage reusable (in both CTAs of a pair) once these MMAs have read it
+                            if (PAIR) tc_commit2(bar_wempty + 8 * st);
+                            else tc_commit(bar_wempty + 8 * st);
                         }
                         __syncwarp();
                     }
                 }
-                if (leader) tc_commit(bar_accfull + 8 * slot);
+                if (leader) {
+                    if (PAIR) tc_commit2(bar_accfull + 8 * slot);
+                    else tc_commit(bar_accfull + 8 * slot);
+                }
                 __syncwarp();
             }
         }
@@ -311,10 +384,19 @@ __global__ void __launch_bounds__(N_THREADS, 1) k_value_tower(const Params p) {
             }
         };
 
+        // the MMA issuer (rank 0 of a pair) learns from both CTAs that a tile's input is in place
+        const uint32_t aready_dst = (PAIR && crank != 0) ? map_to_cta(bar_aready, 0) : bar_aready;
+        auto signal_ready = [&](int slot) {   // every lane has fenced its own writes; one lane reports for the warp
+            __syncwarp();
+            if (lane == 0) {
+                if (PAIR && crank != 0) mbar_arrive_cluster(aready_dst + 8 * slot);
+                else mbar_arrive(aready_dst + 8 * slot);
+            }
+        };
         for (int slot = 0; slot < NT; ++slot) {
             load_planes(slot, 0);
             fence_proxy_async();
-            mbar_arrive(bar_aready + 8 * slot);
+            signal_ready(slot);
         }
 
         const float fm = x != 0 ? 1.f : 0.f, fp = x != G::W - 1 ? 1.f : 0.f;   // horizontal taps that stay on the board
@@ -360,7 +442,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) k_value_tower(const Params p) {
                             xreg[slot][cc * 8 + (i >> 1)] = keep ? pk : xr;
                         }
                     }
-                    if (valid && !last) {
+                    if (valid && !last && !(p.dbg & 2)) {
                         const int chunk = half * 8 + cc * 2;
                         *reinterpret_cast<uint4*>(arow + chunk * A_LBO) = make_uint4(o[0], o[1], o[2], o[3]);
                         *reinterpret_cast<uint4*>(arow + (chunk + 1) * A_LBO) = make_uint4(o[4], o[5], o[6], o[7]);
@@ -397,16 +479,18 @@ __global__ void __launch_bounds__(N_THREADS, 1) k_value_tower(const Params p) {
                 }
                 fence_proxy_async();
                 tc_fence_before();
-                mbar_arrive(bar_aready + 8 * slot);
+                signal_ready(slot);
             }
         }
     }
 
     tc_fence_before();
     __syncthreads();
+    if (PAIR) cluster_sync();   // no CTA leaves while its peer may still use its shared memory, barriers or TMEM
     if (warp == 1) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
+        if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
+        else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
     }
 }
 

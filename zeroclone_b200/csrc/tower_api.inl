@@ -5,6 +5,7 @@
 struct zc_tower {
     int game = 0, device = 0, n_layers = 0, cin = 0;
     uint8_t* wimg = nullptr;
+    uint8_t* wimg2 = nullptr;
     float* bias = nullptr;
     float* head_w = nullptr;
     float head_b = 0.f;
@@ -41,16 +42,22 @@ extern "C" int zc_tower_create(int game, int device, int n_blocks, const float* 
     // weight images in the shared-memory layout of the B operand: [layer][tap][k-chunk][n][8] bf16,
     // taps ordered by column offset first (dx = -1, 0, +1), then row offset (dy = -1, 0, +1).
     // conv_w is PyTorch's [Cout][Cin][kH][kW] per layer, stem first (cross-correlation: dy = kh-1, dx = kw-1).
-    std::vector<uint16_t> img((size_t)nl * 9 * KCHUNKS * CH * 8, 0);
+    // img2 is the same data split by halves of N: [layer][tap][n / 64][k-chunk][n % 64][8], the part of the
+    // B operand each CTA of a cta_group::2 pair keeps in its own shared memory.
+    std::vector<uint16_t> img((size_t)nl * 9 * KCHUNKS * CH * 8, 0), img2(img.size(), 0);
     size_t woff = 0;
     for (int l = 0; l < nl; ++l) {
         const int ci = l == 0 ? cin : CH;
         for (int g = 0; g < 3; ++g)
             for (int dyi = 0; dyi < 3; ++dyi) {
                 uint16_t* dst = img.data() + ((size_t)l * 9 + g * 3 + dyi) * KCHUNKS * CH * 8;
+                uint16_t* dst2 = img2.data() + ((size_t)l * 9 + g * 3 + dyi) * KCHUNKS * CH * 8;
                 for (int n = 0; n < CH; ++n)
-                    for (int k = 0; k < ci; ++k)
-                        dst[((size_t)(k / 8) * CH + n) * 8 + (k % 8)] = f32_to_bf16_rne(conv_w[woff + (((size_t)n * ci + k) * 3 + dyi) * 3 + g]);
+                    for (int k = 0; k < ci; ++k) {
+                        const uint16_t v = f32_to_bf16_rne(conv_w[woff + (((size_t)n * ci + k) * 3 + dyi) * 3 + g]);
+                        dst[((size_t)(k / 8) * CH + n) * 8 + (k % 8)] = v;
+                        dst2[(((size_t)(n / 64) * KCHUNKS + k / 8) * 64 + n % 64) * 8 + (k % 8)] = v;
+                    }
             }
         woff += (size_t)CH * ci * 9;
     }
@@ -62,7 +69,7 @@ extern "C" int zc_tower_create(int game, int device, int n_blocks, const float* 
     t->head_b = head_b;
     t->n_sms = prop.multiProcessorCount;
     auto cleanup = [&](int rc) {
-        cudaFree(t->wimg); cudaFree(t->bias); cudaFree(t->head_w); cudaFree(t->fault);
+        cudaFree(t->wimg); cudaFree(t->wimg2); cudaFree(t->bias); cudaFree(t->head_w); cudaFree(t->fault);
         delete t;
         return rc;
     };
@@ -72,15 +79,19 @@ extern "C" int zc_tower_create(int game, int device, int n_blocks, const float* 
         if (_e != cudaSuccess) return cleanup(fail(ZC_ECUDA, std::string(#expr) + ": " + cudaGetErrorString(_e))); \
     } while (0)
     TOWER_TRY(cudaMalloc(&t->wimg, img.size() * 2));
+    TOWER_TRY(cudaMalloc(&t->wimg2, img2.size() * 2));
     TOWER_TRY(cudaMalloc(&t->bias, sizeof(float) * nl * CH));
     TOWER_TRY(cudaMalloc(&t->head_w, sizeof(float) * CH));
     TOWER_TRY(cudaMalloc(&t->fault, sizeof(unsigned int)));
     TOWER_TRY(cudaMemcpy(t->wimg, img.data(), img.size() * 2, cudaMemcpyHostToDevice));
+    TOWER_TRY(cudaMemcpy(t->wimg2, img2.data(), img2.size() * 2, cudaMemcpyHostToDevice));
     TOWER_TRY(cudaMemcpy(t->bias, conv_b, sizeof(float) * nl * CH, cudaMemcpyHostToDevice));
     TOWER_TRY(cudaMemcpy(t->head_w, head_w, sizeof(float) * CH, cudaMemcpyHostToDevice));
     TOWER_TRY(cudaMemset(t->fault, 0, sizeof(unsigned int)));
-    TOWER_TRY(cudaFuncSetAttribute(k_value_tower<GeomC4>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
-    TOWER_TRY(cudaFuncSetAttribute(k_value_tower<GeomChess>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
+    TOWER_TRY(cudaFuncSetAttribute(k_value_tower<GeomC4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
+    TOWER_TRY(cudaFuncSetAttribute(k_value_tower<GeomC4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
+    TOWER_TRY(cudaFuncSetAttribute(k_value_tower<GeomChess, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
+    TOWER_TRY(cudaFuncSetAttribute(k_value_tower<GeomChess, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
 #undef TOWER_TRY
     *out = t;
     return ZC_OK;
@@ -90,6 +101,7 @@ extern "C" void zc_tower_destroy(zc_tower* t) {
     if (!t) return;
     cudaSetDevice(t->device);
     cudaFree(t->wimg);
+    cudaFree(t->wimg2);
     cudaFree(t->bias);
     cudaFree(t->head_w);
     cudaFree(t->fault);
@@ -105,6 +117,7 @@ extern "C" int zc_tower_forward(zc_tower* t, const void* dev_planes_bf16, int n_
     Params p;
     p.planes = reinterpret_cast<const __nv_bfloat16*>(dev_planes_bf16);
     p.wimg = t->wimg;
+    p.wimg2 = t->wimg2;
     p.bias = t->bias;
     p.head_w = t->head_w;
     p.head_b = t->head_b;
@@ -112,13 +125,30 @@ extern "C" int zc_tower_forward(zc_tower* t, const void* dev_planes_bf16, int n_
     p.n_leaves = n_leaves;
     p.n_layers = t->n_layers;
     p.fault = t->fault;
+    p.dbg = getenv("ZC_TOWER_DEBUG") ? atoi(getenv("ZC_TOWER_DEBUG")) : 0;
     const int nb = t->game == ZC_GAME_C4 ? GeomC4::NB : GeomChess::NB;
     const int n_groups = (n_leaves + nb - 1) / nb;
-    const int grid = std::max(1, std::min(t->n_sms, (n_groups + NT - 1) / NT));
+    const bool pair = getenv("ZC_TOWER_PAIR") ? atoi(getenv("ZC_TOWER_PAIR")) != 0 : true;
+    const int csz = pair ? 2 : 1;
+    int grid = std::max(1, std::min(t->n_sms, (n_groups + NT - 1) / NT));
+    grid = std::max(csz, grid / csz * csz);            // whole pairs
     cudaStream_t st = (cudaStream_t)stream;
-    if (t->game == ZC_GAME_C4) k_value_tower<GeomC4><<<grid, N_THREADS, SMEM_TOTAL, st>>>(p);
-    else k_value_tower<GeomChess><<<grid, N_THREADS, SMEM_TOTAL, st>>>(p);
-    CUDA_TRY(cudaGetLastError());
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(N_THREADS);
+    cfg.dynamicSmemBytes = SMEM_TOTAL;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)csz;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    const bool c4 = t->game == ZC_GAME_C4;
+    void (*kern)(const Params) = pair ? (c4 ? k_value_tower<GeomC4, true> : k_value_tower<GeomChess, true>)
+                                      : (c4 ? k_value_tower<GeomC4, false> : k_value_tower<GeomChess, false>);
+    CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, p));
     ++t->launches;
     return ZC_OK;
 }
