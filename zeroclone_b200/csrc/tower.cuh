@@ -208,9 +208,9 @@ __global__ void __launch_bounds__(N_THREADS, 1) k_value_tower(const Params p) {
     constexpr uint32_t STAGE_BYTES = RING_BYTES / NSTAGE;        // a whole tap image, or this CTA's half of it
     constexpr uint32_t BLBO = PAIR ? B_LBO / 2 : B_LBO;          // k-chunk stride of the B operand held here
     const uint32_t bar_wfull = sbase + SMEM_BARS, bar_wempty = bar_wfull + 8 * NSTAGE, bar_aready = bar_wempty + 8 * NSTAGE,
-                   bar_accfull = bar_aready + 8 * NT, bar_wpeer = bar_accfull + 8 * NT;
-    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + SMEM_BARS + 8 * (3 * NSTAGE + 2 * NT));
-    static_assert(8 * (3 * 8 + 2 * NT) + 4 <= SMEM_PART, "barrier area");
+                   bar_accfull = bar_aready + 8 * NT, bar_pfree = bar_accfull + 8 * NT, bar_wpeer = bar_pfree + 8 * NT;
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + SMEM_BARS + 8 * (3 * NSTAGE + 3 * NT));
+    static_assert(8 * (3 * 8 + 3 * NT) + 4 <= SMEM_PART, "barrier area");
     float* part = reinterpret_cast<float*>(smem + SMEM_PART);
 
     // this CTA's share of board groups and the (identical) step sequence every role walks
@@ -237,6 +237,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) k_value_tower(const Params p) {
         for (int t = 0; t < NT; ++t) {
             mbar_init(bar_aready + 8 * t, (PAIR ? 2 : 1) * N_EPI_WARPS);   // one arrival per epilogue warp; pair: both CTAs report to rank 0
             mbar_init(bar_accfull + 8 * t, 1);
+            mbar_init(bar_pfree + 8 * t, (PAIR ? 2 : 1) * N_EPI_WARPS);    // side accumulators of a step have been read
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -305,12 +306,21 @@ __global__ void __launch_bounds__(N_THREADS, 1) k_value_tower(const Params p) {
                 const uint32_t abuf = sbase + SMEM_ABUF + slot * A_BUF_BYTES + HALO * 16;
 #pragma unroll 1
                 for (int g = 0; g < 3; ++g, ++gcnt) {
-                    if (NT == 2 && g == 1 && n >= 1 && !(p.dbg & 1)) {
-                        // accumulators (gcnt % 4) of this and the next group were last used by the previous
-                        // step; its epilogue signals through the a_ready of the step after this one
-                        const int n1 = n + 1;
-                        mbar_wait(bar_aready + 8 * (n1 % NT), (uint32_t)(n1 / NT) & 1u, p.fault, 3);
-                        tc_fence_after();
+                    // Accumulator gcnt % 4 was last used three groups ago, by the previous step: group 1 takes over
+                    // that step's dx = -1 accumulator, which its epilogue reads first and releases early (pfree);
+                    // group 2 takes over its dx = 0 accumulator, free when that epilogue is complete, which it
+                    // reports through the a_ready of the step after this one.  (Group 0 reuses an accumulator of
+                    // the step before the previous one, released long ago.)
+                    if (NT == 2 && n >= 1 && !(p.dbg & 1)) {
+                        if (g == 1) {
+                            const int n0 = n - 1;
+                            mbar_wait(bar_pfree + 8 * (n0 % NT), (uint32_t)(n0 / NT) & 1u, p.fault, 3);
+                            tc_fence_after();
+                        } else if (g == 2) {
+                            const int n1 = n + 1;
+                            mbar_wait(bar_aready + 8 * (n1 % NT), (uint32_t)(n1 / NT) & 1u, p.fault, 8);
+                            tc_fence_after();
+                        }
                     }
                     const uint32_t acc = tmem + (gcnt & 3u) * 128u;
 #pragma unroll 1
@@ -386,13 +396,15 @@ __global__ void __launch_bounds__(N_THREADS, 1) k_value_tower(const Params p) {
 
         // the MMA issuer (rank 0 of a pair) learns from both CTAs that a tile's input is in place
         const uint32_t aready_dst = (PAIR && crank != 0) ? map_to_cta(bar_aready, 0) : bar_aready;
-        auto signal_ready = [&](int slot) {   // every lane has fenced its own writes; one lane reports for the warp
+        const uint32_t pfree_dst = (PAIR && crank != 0) ? map_to_cta(bar_pfree, 0) : bar_pfree;
+        auto signal = [&](uint32_t bar) {   // every lane has fenced its own accesses; one lane reports for the warp
             __syncwarp();
             if (lane == 0) {
-                if (PAIR && crank != 0) mbar_arrive_cluster(aready_dst + 8 * slot);
-                else mbar_arrive(aready_dst + 8 * slot);
+                if (PAIR && crank != 0) mbar_arrive_cluster(bar);
+                else mbar_arrive(bar);
             }
         };
+        auto signal_ready = [&](int slot) { signal(aready_dst + 8 * slot); };
         for (int slot = 0; slot < NT; ++slot) {
             load_planes(slot, 0);
             fence_proxy_async();
@@ -412,13 +424,26 @@ __global__ void __launch_bounds__(N_THREADS, 1) k_value_tower(const Params p) {
                 mbar_wait(bar_accfull + 8 * slot, (uint32_t)m & 1u, p.fault, 5);
                 tc_fence_after();
                 uint8_t* arow = smem + SMEM_ABUF + slot * A_BUF_BYTES + (HALO + r) * 16;
+                // phase 1: the two side accumulators (dx = -1, +1), masked at the board edges, into registers;
+                // their TMEM columns go back to the MMA issuer before the rest of the epilogue runs
+                float side[64];
 #pragma unroll
                 for (int cc = 0; cc < 4; ++cc) {
                     const uint32_t col = half * 64 + cc * 16;
-                    uint32_t am[16], a0[16], ap[16];
+                    uint32_t am[16], ap[16];
                     tc_ld16(tlane + ((gbase + 0) & 3u) * 128u + col, am);
-                    tc_ld16(tlane + ((gbase + 1) & 3u) * 128u + col, a0);
                     tc_ld16(tlane + ((gbase + 2) & 3u) * 128u + col, ap);
+                    tc_wait_ld();
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) side[cc * 16 + i] = fmaf(fp, __uint_as_float(ap[i]), fm * __uint_as_float(am[i]));
+                }
+                tc_fence_before();
+                signal(pfree_dst + 8 * slot);
+#pragma unroll
+                for (int cc = 0; cc < 4; ++cc) {
+                    const uint32_t col = half * 64 + cc * 16;
+                    uint32_t a0[16];
+                    tc_ld16(tlane + ((gbase + 1) & 3u) * 128u + col, a0);
                     tc_wait_ld();
                     uint32_t o[8];
 #pragma unroll
@@ -429,10 +454,8 @@ __global__ void __launch_bounds__(N_THREADS, 1) k_value_tower(const Params p) {
                         for (int e = 0; e < 4; e += 2) {
                             const int i = q * 4 + e;
                             const uint32_t xr = xreg[slot][cc * 8 + (i >> 1)];
-                            float v0 = fmaf(fm, __uint_as_float(am[i]), __uint_as_float(a0[i]));
-                            float v1 = fmaf(fm, __uint_as_float(am[i + 1]), __uint_as_float(a0[i + 1]));
-                            v0 = fmaf(fp, __uint_as_float(ap[i]), v0);
-                            v1 = fmaf(fp, __uint_as_float(ap[i + 1]), v1);
+                            float v0 = __uint_as_float(a0[i]) + side[cc * 16 + i];
+                            float v1 = __uint_as_float(a0[i + 1]) + side[cc * 16 + i + 1];
                             v0 += bv[e];
                             v1 += bv[e + 1];
                             v0 = fmaf(fres, bf16_lo(xr), v0);
