@@ -108,7 +108,7 @@ class ClockSampler:
 # our arm
 # ----------------------------------------------------------------------------------------------
 # dram__bytes_read.sum + dram__bytes_write.sum per evaluated leaf, from the ncu captures under profiles/
-TOWER_DRAM_BYTES_PER_LEAF = {"connect4": 229.2, "chess": 2400.0}
+TOWER_DRAM_BYTES_PER_LEAF = {"connect4": 205.3, "chess": 2334.1}
 
 
 def run_ours(args):
@@ -265,7 +265,7 @@ def run_ours(args):
         ach = fl / (net_ms * 1e-3) / 1e12
         roofline = {"bound": "tensor", "achieved": ach, "peak": tensor_peak, "unit": "TFLOP/s", "frac": ach / tensor_peak,
                     # dram__bytes_read+write of one `ncu --set full` capture of k_value_tower per leaf
-                    # (profiles/r1d_k_value_tower_c4_ncu.txt): planes in, values out, weights from L2
+                    # (profiles/r1d_k_value_tower_{c4,chess}_ncu.txt): planes in, values out, weights from L2
                     "traffic": TOWER_DRAM_BYTES_PER_LEAF[wl["game"]] * sims_done / (sims // BATCH + (1 if sims % BATCH else 0)),
                     "traffic_source": "ncu capture of k_value_tower at 131072 leaves, scaled per leaf",
                     "kernel": "k_value_tower (fused tcgen05 residual tower, bf16 x bf16 -> fp32), %d launches" % n_net,
