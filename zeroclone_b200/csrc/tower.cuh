@@ -96,7 +96,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, unsigne
         if ((it & 1023u) == 1023u) {
             const long long now = clock64();
             if (t0 == 0) t0 = now;
-            else if (now - t0 > 4000000000ll) {   // ~2 s
+            else if (now - t0 > 20000000000ll) {   // ~10 s
                 atomicExch(fault, 0x80000000u | (unsigned)tag);
                 __threadfence_system();
                 __trap();
