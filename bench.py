@@ -175,7 +175,7 @@ def run_ours(args):
                 timed("tree", lambda: ts.run(sims, C_UCT, BATCH, heur, _ffi.POLICY_FIRST, 0, stream))
             else:
                 ts.run(sims, C_UCT, BATCH, heur, _ffi.POLICY_FIRST, 0, stream)
-        return ts.results(stats=False, stream=stream)
+        return ts.results(stats=False, stream=stream, reuse=True)
 
     def run_network_timed():
         planes, values = ts._planes, ts._values
@@ -192,7 +192,7 @@ def run_ours(args):
             ts.run_network(ev, sims, C_UCT, BATCH, _ffi.POLICY_FIRST)
         else:
             ts.run(sims, C_UCT, BATCH, heur, _ffi.POLICY_FIRST, 0, stream)
-        return ts.results(stats=False, stream=stream)    # what get_move returns: the chosen move per tree (mcts.cpp:157-159)
+        return ts.results(stats=False, stream=stream, reuse=True)    # what get_move returns: the chosen move per tree (mcts.cpp:157-159)
 
     def barrier():
         if world > 1:

@@ -52,6 +52,7 @@ struct zc_search {
     uint16_t* scratch = nullptr;        // chess move staging, one buffer per lane
     void* roots_dev = nullptr;          // staging for host roots
     zc_root_result* res_dev = nullptr;
+    zc_root_result* res_host = nullptr;  // pinned staging of the per-tree results
     int32_t* visits_dev = nullptr;
     double* wsum_dev = nullptr;
     zc_chess_move* moves_dev = nullptr;
@@ -323,6 +324,7 @@ extern "C" int zc_search_create(int game, int device, int max_trees, int max_sim
     if (e == cudaSuccess) e = alloc((void**)&h->work_counter, sizeof(unsigned int));
     if (e == cudaSuccess) e = alloc((void**)&h->roots_dev, sizeof(zc_chess_state) * max_trees);
     if (e == cudaSuccess) e = alloc((void**)&h->res_dev, sizeof(zc_root_result) * max_trees);
+    if (e == cudaSuccess) e = cudaMallocHost((void**)&h->res_host, sizeof(zc_root_result) * max_trees);
     if (e == cudaSuccess) e = alloc((void**)&h->hash_dev, sizeof(unsigned long long) * max_trees);
     if (e != cudaSuccess) {
         std::string msg = std::string("cudaMalloc: ") + cudaGetErrorString(e);
@@ -371,6 +373,7 @@ extern "C" int zc_search_destroy(zc_search* h) {
     cudaFree(h->scratch);
     cudaFree(h->roots_dev);
     cudaFree(h->res_dev);
+    cudaFreeHost(h->res_host);
     cudaFree(h->visits_dev);
     cudaFree(h->wsum_dev);
     cudaFree(h->moves_dev);
@@ -553,11 +556,12 @@ extern "C" int zc_search_results(zc_search* h, zc_root_result* results, int32_t*
                                                        moves ? h->moves_dev : nullptr, stride);
     h->launches++;
     CUDA_TRY(cudaGetLastError());
-    CUDA_TRY(cudaMemcpyAsync(results, h->res_dev, sizeof(zc_root_result) * n, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(h->res_host, h->res_dev, sizeof(zc_root_result) * n, cudaMemcpyDeviceToHost, st));
     if (visits) CUDA_TRY(cudaMemcpyAsync(visits, h->visits_dev, sizeof(int32_t) * (size_t)n * stride, cudaMemcpyDeviceToHost, st));
     if (value_sums) CUDA_TRY(cudaMemcpyAsync(value_sums, h->wsum_dev, sizeof(double) * (size_t)n * stride, cudaMemcpyDeviceToHost, st));
     if (moves) CUDA_TRY(cudaMemcpyAsync(moves, h->moves_dev, sizeof(zc_chess_move) * (size_t)n * stride, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
+    memcpy(results, h->res_host, sizeof(zc_root_result) * (size_t)n);
     for (int i = 0; i < n; ++i)
         if (results[i].status != 0) return fail(ZC_ECAPACITY, "tree " + std::to_string(i) + " outgrew its arena");
     return ZC_OK;

@@ -109,9 +109,16 @@ class TreeSearch:
                 self.backprop(self._values.data_ptr(), stream)
 
     # -- readout ---------------------------------------------------------------------------------
-    def results(self, stats: bool = True, stream=None) -> dict:
+    def results(self, stats: bool = True, stream=None, reuse: bool = False) -> dict:
+        """Root readout (mcts.cpp:150-159).  reuse=True returns the per-tree result array owned by this
+        object (overwritten by the next call) instead of a fresh one -- fresh pages cost more than the copy."""
         n = self.n_trees
-        res = np.zeros(n, dtype=ROOT_RESULT_DTYPE)
+        if reuse:
+            if getattr(self, "_res_buf", None) is None or len(self._res_buf) < n:
+                self._res_buf = np.zeros(self.max_trees, dtype=ROOT_RESULT_DTYPE)
+            res = self._res_buf[:n]
+        else:
+            res = np.zeros(n, dtype=ROOT_RESULT_DTYPE)
         visits = wsum = moves = None
         stride = self.max_moves
         if stats:
