@@ -99,6 +99,12 @@ def test_tower_full_batch_size():
         ref = model(x[idx]).view(-1)
     assert (got[idx] - ref).abs().max().item() < TOL
     assert torch.isfinite(got).all()
+    # the CTA-pair / two-tiles-in-flight pipeline must not depend on timing: bit-identical reruns, and the
+    # same bits as evaluating a slice on its own (different CTA, tile slot and pair rank for every leaf)
+    xd = x.to("cuda", torch.bfloat16)
+    for _ in range(3):
+        assert torch.equal(ev(xd).cpu(), got)
+    assert torch.equal(ev(xd[70001:70001 + 5000].contiguous()).cpu(), got[70001:70001 + 5000])
 
 
 def test_tower_rejects_what_it_cannot_compute():

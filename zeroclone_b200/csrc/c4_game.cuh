@@ -7,6 +7,7 @@
 namespace zc {
 
 struct C4Game {
+    static constexpr int kMinBlocks = 7;   // resident 128-thread blocks per SM the fused search is compiled for
     using State = c4::State;
     static constexpr int SS = 1;            // state slots per node
     static constexpr int FIRST_SLOTS = 9;   // header + state + up to 7 edges: the whole node in one warp load

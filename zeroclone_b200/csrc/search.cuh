@@ -563,8 +563,8 @@ constexpr int SEARCH_BLOCK = 128;
 
 // Fused persistent search with a built-in evaluator: the whole simulation loop of get_move
 // (mcts.cpp:129-149) for every tree.  Warps pull tree indices from a global counter.
-template <class G>
-__global__ void __launch_bounds__(SEARCH_BLOCK) k_search_fused(SearchParams p) {
+template <class G, int MINB = G::kMinBlocks>
+__global__ void __launch_bounds__(SEARCH_BLOCK, MINB) k_search_fused(SearchParams p) {
     __shared__ WarpPlan plans[SEARCH_BLOCK / 32];
     WarpPlan& wp = plans[threadIdx.x >> 5];
     const int lane = threadIdx.x & 31;
