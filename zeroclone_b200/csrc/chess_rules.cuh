@@ -66,19 +66,28 @@ ZC_HD int capture_value(int code) {
 // order (chess_backend.cpp:27-30):  0 (-1,-1)  1 (-1,+1)  2 (+1,-1)  3 (+1,+1)  4 (-1,0)  5 (+1,0)  6 (0,-1)  7 (0,+1)
 #include "chess_tables.inc"
 #ifdef __CUDACC__
-__device__ const uint64_t d_rays[8][64] = ZC_RAY_TABLE;
+__device__ __align__(64) const uint64_t d_rays_t[64][8] = ZC_RAY_TABLE_T;
 __device__ const uint64_t d_knight[64] = ZC_KNIGHT_TABLE;
 __device__ const uint64_t d_king[64] = ZC_KING_TABLE;
 #endif
-static const uint64_t h_rays[8][64] = ZC_RAY_TABLE;
+alignas(64) static const uint64_t h_rays_t[64][8] = ZC_RAY_TABLE_T;
 static const uint64_t h_knight[64] = ZC_KNIGHT_TABLE;
 static const uint64_t h_king[64] = ZC_KING_TABLE;
 
-ZC_HD uint64_t ray_beyond(int d, int sq) {
+// r[d] = squares strictly beyond sq in direction d (d in [D0, D0 + N)): the rays of a square share one
+// 64-byte line, fetched with independent 16-byte loads so a caller pays the load latency once
+template <int D0, int N>
+ZC_HD void rays_of(int sq, uint64_t* r) {
 #ifdef __CUDA_ARCH__
-    return d_rays[d][sq];
+    const ulonglong2* line = reinterpret_cast<const ulonglong2*>(&d_rays_t[sq][D0]);
+#pragma unroll
+    for (int i = 0; i < N / 2; ++i) {
+        const ulonglong2 v = __ldg(line + i);
+        r[2 * i] = v.x;
+        r[2 * i + 1] = v.y;
+    }
 #else
-    return h_rays[d][sq];
+    for (int i = 0; i < N; ++i) r[i] = h_rays_t[sq][D0 + i];
 #endif
 }
 ZC_HD uint64_t knight_targets(int sq) {
@@ -96,41 +105,37 @@ ZC_HD uint64_t king_targets(int sq) {
 #endif
 }
 // directions along which the square index grows
-ZC_HD bool dir_ascending(int d) { return d == 2 || d == 3 || d == 5 || d == 7; }
-// first occupied square of a non-empty subset of a ray, seen from the ray's origin
-ZC_HD int first_on_ray(int d, uint64_t blockers) { return dir_ascending(d) ? zc_ctz64(blockers) : 63 - zc_clz64(blockers); }
-// squares reachable from sq along d, up to and including the first blocker
-ZC_HD uint64_t ray_dir(int d, int sq, uint64_t occ) {
-    uint64_t r = ray_beyond(d, sq);
-    const uint64_t b = r & occ;
-    if (b) r &= ~ray_beyond(d, first_on_ray(d, b));
-    return r;
+ZC_HD constexpr bool dir_ascending(int d) { return d == 2 || d == 3 || d == 5 || d == 7; }
+// the first occupied square met along a ray, as a one-bit mask (0 if the ray is empty): lowest blocker for
+// an ascending direction, highest for a descending one
+ZC_HD uint64_t first_blocker(int d, uint64_t blockers) {
+    if (dir_ascending(d)) return blockers & (0 - blockers);
+    return blockers ? bit(63 - zc_clz64(blockers)) : 0ull;
 }
-// is the first piece met from sq along d a member of `attackers` (a subset of occ)?
-ZC_HD bool ray_hits(int d, int sq, uint64_t occ, uint64_t attackers) {
-    const uint64_t r = ray_beyond(d, sq);
-    if (!(r & attackers)) return false;
-    return (attackers >> first_on_ray(d, r & occ)) & 1ull;
+// squares of `ray` (the squares beyond some origin in direction d) up to and including the first blocker
+ZC_HD uint64_t ray_until_blocker(int d, uint64_t ray, uint64_t occ) {
+    const uint64_t f = first_blocker(d, ray & occ);
+    if (dir_ascending(d)) return ray & ((f << 1) - 1);          // f == 0: (0 << 1) - 1 keeps the whole ray
+    return f ? ray & ~(f - 1) : ray;
 }
 
 // chess_backend.cpp:85-144 -- is the king of `side` on square ksq attacked, given the enemy sets
-// (all subsets of occ)?
+// (all subsets of occ)?  Branch-free over the eight rays: the first piece met along a ray attacks iff it
+// is an enemy slider of that ray's kind.
 ZC_HD bool square_attacked(int side, int ksq, uint64_t occ, uint64_t e_pawn, uint64_t e_knight, uint64_t e_diag,
                            uint64_t e_orth, uint64_t e_king) {
     const uint64_t k = bit(ksq);
     // pawns: a white king looks one row up (r-1) for 'p', a black king one row down for 'P'
     const uint64_t pawn_from = side == 0 ? (((k >> 9) & ~FILE_H) | ((k >> 7) & ~FILE_A))
                                          : (((k << 7) & ~FILE_H) | ((k << 9) & ~FILE_A));
-    if (pawn_from & e_pawn) return true;
-    if (knight_targets(ksq) & e_knight) return true;
-    if (king_targets(ksq) & e_king) return true;
-    if (e_diag)
-        for (int d = 0; d < 4; ++d)
-            if (ray_hits(d, ksq, occ, e_diag)) return true;
-    if (e_orth)
-        for (int d = 4; d < 8; ++d)
-            if (ray_hits(d, ksq, occ, e_orth)) return true;
-    return false;
+    uint64_t hit = (pawn_from & e_pawn) | (knight_targets(ksq) & e_knight) | (king_targets(ksq) & e_king);
+    if (e_diag | e_orth) {
+        uint64_t r[8];
+        rays_of<0, 8>(ksq, r);
+#pragma unroll
+        for (int d = 0; d < 8; ++d) hit |= first_blocker(d, r[d] & occ) & (d < 4 ? e_diag : e_orth);
+    }
+    return hit != 0;
 }
 
 struct Sets {   // derived once per position
@@ -233,12 +238,15 @@ ZC_HD int generate(const Board& b, int turn, uint16_t* out) {
                 if (targets_ok >> t & 1) out[n++] = (uint16_t)(pack_move(sq, t) | MOVE_KING_FLAG);
             }
         } else if (type == BISHOP || type == ROOK || type == QUEEN) {   // :278-319
+            uint64_t rr[8];
+            rays_of<0, 8>(sq, rr);
             const int d0 = type == ROOK ? 4 : 0, d1 = type == BISHOP ? 4 : 8;
-            for (int d = d0; d < d1; ++d) {
-                uint64_t tg = ray_dir(d, sq, s.occ) & targets_ok;
-                const bool asc = dir_ascending(d);
+#pragma unroll
+            for (int d = 0; d < 8; ++d) {
+                if (d < d0 || d >= d1) continue;
+                uint64_t tg = ray_until_blocker(d, rr[d], s.occ) & targets_ok;
                 while (tg) {                                            // outward from the piece
-                    const int t = asc ? zc_ctz64(tg) : 63 - zc_clz64(tg);
+                    const int t = dir_ascending(d) ? zc_ctz64(tg) : 63 - zc_clz64(tg);
                     tg &= ~bit(t);
                     out[n++] = pack_move(sq, t);
                 }
