@@ -138,6 +138,32 @@ ZC_HD bool square_attacked(int side, int ksq, uint64_t occ, uint64_t e_pawn, uin
     return hit != 0;
 }
 
+// The same test for the side to move's king in the current position, plus the own pieces PINNED to it: the
+// first piece met along a ray is own and the second is an enemy slider of that ray's kind.  Only such a
+// piece can expose the king by leaving its square (legality filter, chess_backend.cpp:345-358).
+ZC_HD bool king_danger(int side, int ksq, uint64_t occ, uint64_t own, uint64_t e_pawn, uint64_t e_knight, uint64_t e_diag,
+                       uint64_t e_orth, uint64_t e_king, uint64_t& pinned) {
+    const uint64_t k = bit(ksq);
+    const uint64_t pawn_from = side == 0 ? (((k >> 9) & ~FILE_H) | ((k >> 7) & ~FILE_A))
+                                         : (((k << 7) & ~FILE_H) | ((k << 9) & ~FILE_A));
+    uint64_t hit = (pawn_from & e_pawn) | (knight_targets(ksq) & e_knight) | (king_targets(ksq) & e_king);
+    uint64_t pins = 0;
+    if (e_diag | e_orth) {
+        uint64_t r[8];
+        rays_of<0, 8>(ksq, r);
+#pragma unroll
+        for (int d = 0; d < 8; ++d) {
+            const uint64_t sliders = d < 4 ? e_diag : e_orth;
+            if (!(r[d] & sliders)) continue;                     // no such slider on this ray at all
+            const uint64_t b = r[d] & occ, f1 = first_blocker(d, b);
+            hit |= f1 & sliders;
+            if (first_blocker(d, b & ~f1) & sliders) pins |= f1 & own;
+        }
+    }
+    pinned = pins;
+    return hit != 0;
+}
+
 struct Sets {   // derived once per position
     uint64_t occ, own, enemy, e_pawn, e_knight, e_bishop, e_rook, e_queen, e_king, own_king;
 };
@@ -190,9 +216,10 @@ ZC_HD int move_to(uint16_t m) { return (m >> 6) & 63; }
 //
 // Pass 1 emits the pseudo-legal moves in the reference's scan order (:203-342).  Pass 2 is the
 // reference's stable legality filter (:345-358) with ONE call site of the attack test and an exact
-// shortcut: if the mover is not in check, a non-king piece that does not stand on a rank, file or
-// diagonal through its king cannot expose the king by leaving its square (its destination can only
-// block lines, a capture only removes an attacker), so such a move is legal without testing.
+// shortcut: if the mover is not in check, a non-king piece can expose its king by leaving its square only
+// if it is pinned (alone between the king and an enemy slider on a line the slider moves along); its
+// destination can only block lines and a capture only removes an attacker.  So unpinned pieces' moves
+// are legal without testing; king moves, pinned pieces and every move while in check take the full test.
 constexpr int MAX_PSEUDO = 256;
 constexpr uint16_t MOVE_KING_FLAG = 1u << 12;
 
@@ -259,18 +286,16 @@ ZC_HD int generate(const Board& b, int turn, uint16_t* out) {
         return n;
     }
     const int ksq = zc_ctz64(s.own_king);    // find_king: the first king in index order (:68-81)
-    const int kr = ksq >> 3, kc = ksq & 7;
-    const bool checked = square_attacked(turn, ksq, s.occ, s.e_pawn, s.e_knight, s.e_bishop | s.e_queen,
-                                         s.e_rook | s.e_queen, s.e_king);
+    uint64_t pinned;
+    const bool checked = king_danger(turn, ksq, s.occ, s.own, s.e_pawn, s.e_knight, s.e_bishop | s.e_queen,
+                                     s.e_rook | s.e_queen, s.e_king, pinned);
     int m = 0;
     for (int i = 0; i < n; ++i) {
         const uint16_t mv = out[i];
         const int from = mv & 63, to = (mv >> 6) & 63;
         const bool king_moves = (mv & MOVE_KING_FLAG) != 0;
-        const int dr = (from >> 3) - kr, dc = (from & 7) - kc;
-        const bool aligned = dr == 0 || dc == 0 || dr == dc || dr == -dc;
         bool ok = true;
-        if (checked || king_moves || aligned) ok = move_keeps_king_safe(s, turn, from, to, king_moves);
+        if (checked || king_moves || (pinned >> from & 1)) ok = move_keeps_king_safe(s, turn, from, to, king_moves);
         if (ok) out[m++] = (uint16_t)(mv & 0x0FFF);
     }
     return m;
