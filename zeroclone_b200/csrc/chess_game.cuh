@@ -16,11 +16,13 @@ struct ChessGame {
     static constexpr int MOVE_SCRATCH = chess::MAX_PSEUDO;   // pseudo-legal staging (>= 218 legal), multiple of 8
 
     struct Ctx {
-        uint16_t* moves;   // this lane's move buffer
+        uint16_t* moves;   // this lane's move list: entry i at moves[i * stride]
+        int stride;        // 32 in the search: the lanes of a warp interleave their lists, lane-parallel accesses coalesce
     };
     ZC_D static Ctx make_ctx(const SearchParams& p, unsigned warp_slot, int lane) {
         Ctx c;
-        c.moves = p.scratch + ((size_t)warp_slot * 32 + (size_t)lane) * MOVE_SCRATCH;
+        c.moves = p.scratch + (size_t)warp_slot * 32 * MOVE_SCRATCH + (size_t)lane;
+        c.stride = 32;
         return c;
     }
     ZC_D static State state_from_lanes(const uint4& v) {
@@ -67,11 +69,18 @@ struct ChessGame {
         return chess::play(parent, pmisc, chess::move_from(m), chess::move_to(m), cmisc);
     }
     ZC_HD static int count_moves(Ctx& gx, const State& s, uint32_t misc) {
-        return chess::generate(s, (int)(misc & chess::MISC_TURN), gx.moves);
+        return chess::generate(s, (int)(misc & chess::MISC_TURN), gx.moves, gx.stride);
     }
     ZC_HD static void store_moves(Ctx& gx, uint4* dst, int k) {
-        const uint4* src = reinterpret_cast<const uint4*>(gx.moves);
-        for (int i = 0; i < move_slots(k); ++i) dst[i] = src[i];
+        for (int i = 0; i < move_slots(k); ++i) {
+            uint32_t w[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {      // entries beyond k are whatever the staging holds; never read back
+                const uint32_t lo = gx.moves[(size_t)(8 * i + 2 * e) * gx.stride], hi = gx.moves[(size_t)(8 * i + 2 * e + 1) * gx.stride];
+                w[e] = lo | (hi << 16);
+            }
+            dst[i] = make_uint4(w[0], w[1], w[2], w[3]);
+        }
     }
     ZC_HD static double eval(const State& s, uint32_t misc, int, uint64_t) { return chess::crude_score(s, (int)(misc & 1u), 0); }
     ZC_HD static double eval_child(const State& s, uint32_t misc, int k, int, uint64_t) { return chess::crude_score(s, (int)(misc & 1u), k); }

@@ -223,7 +223,9 @@ ZC_HD int move_to(uint16_t m) { return (m >> 6) & 63; }
 constexpr int MAX_PSEUDO = 256;
 constexpr uint16_t MOVE_KING_FLAG = 1u << 12;
 
-ZC_HD int generate(const Board& b, int turn, uint16_t* out) {
+// `stride`: distance between consecutive entries of out[] (32 when the lanes of a warp interleave their lists so
+// that lane-parallel accesses to entry i coalesce)
+ZC_HD int generate(const Board& b, int turn, uint16_t* out, int stride = 1) {
     if (insufficient_material(b)) return 0;
     const Sets s = derive(b, turn);
     const uint64_t empty = ~s.occ;
@@ -240,20 +242,20 @@ ZC_HD int generate(const Board& b, int turn, uint16_t* out) {
             if (nr >= 0 && nr < 8) {
                 const int one = nr * 8 + c;
                 if (empty >> one & 1) {
-                    out[n++] = pack_move(sq, one);
+                    out[(n++) * stride] = pack_move(sq, one);
                     const int two = one + dir * 8;
-                    if (r == home && (empty >> two & 1)) out[n++] = pack_move(sq, two);
+                    if (r == home && (empty >> two & 1)) out[(n++) * stride] = pack_move(sq, two);
                 }
                 const uint64_t capturable = s.enemy & ~s.e_king;
-                if (c > 0 && (capturable >> (one - 1) & 1)) out[n++] = pack_move(sq, one - 1);
-                if (c < 7 && (capturable >> (one + 1) & 1)) out[n++] = pack_move(sq, one + 1);
+                if (c > 0 && (capturable >> (one - 1) & 1)) out[(n++) * stride] = pack_move(sq, one - 1);
+                if (c < 7 && (capturable >> (one + 1) & 1)) out[(n++) * stride] = pack_move(sq, one + 1);
             }
         } else if (type == KNIGHT) {                                    // :255-275; knight_dirs order == ascending target
             uint64_t tg = knight_targets(sq) & targets_ok;
             while (tg) {
                 const int t = zc_ctz64(tg);
                 tg &= tg - 1;
-                out[n++] = pack_move(sq, t);
+                out[(n++) * stride] = pack_move(sq, t);
             }
         } else if (type == KING) {                                      // :322-340, king_dirs order (:31-34)
             for (int d = 0; d < 8; ++d) {
@@ -262,7 +264,7 @@ ZC_HD int generate(const Board& b, int turn, uint16_t* out) {
                 const int rr = r + dr, cc = c + dc;
                 if (rr < 0 || rr > 7 || cc < 0 || cc > 7) continue;
                 const int t = rr * 8 + cc;
-                if (targets_ok >> t & 1) out[n++] = (uint16_t)(pack_move(sq, t) | MOVE_KING_FLAG);
+                if (targets_ok >> t & 1) out[(n++) * stride] = (uint16_t)(pack_move(sq, t) | MOVE_KING_FLAG);
             }
         } else if (type == BISHOP || type == ROOK || type == QUEEN) {   // :278-319
             uint64_t rr[8];
@@ -275,14 +277,14 @@ ZC_HD int generate(const Board& b, int turn, uint16_t* out) {
                 while (tg) {                                            // outward from the piece
                     const int t = dir_ascending(d) ? zc_ctz64(tg) : 63 - zc_clz64(tg);
                     tg &= ~bit(t);
-                    out[n++] = pack_move(sq, t);
+                    out[(n++) * stride] = pack_move(sq, t);
                 }
             }
         }
     }
     // ---- pass 2: legality filter, stable, in place
     if (!s.own_king) {                       // a side without a king is never "in check"
-        for (int i = 0; i < n; ++i) out[i] &= 0x0FFF;
+        for (int i = 0; i < n; ++i) out[i * stride] &= 0x0FFF;
         return n;
     }
     const int ksq = zc_ctz64(s.own_king);    // find_king: the first king in index order (:68-81)
@@ -291,12 +293,12 @@ ZC_HD int generate(const Board& b, int turn, uint16_t* out) {
                                      s.e_rook | s.e_queen, s.e_king, pinned);
     int m = 0;
     for (int i = 0; i < n; ++i) {
-        const uint16_t mv = out[i];
+        const uint16_t mv = out[i * stride];
         const int from = mv & 63, to = (mv >> 6) & 63;
         const bool king_moves = (mv & MOVE_KING_FLAG) != 0;
         bool ok = true;
         if (checked || king_moves || (pinned >> from & 1)) ok = move_keeps_king_safe(s, turn, from, to, king_moves);
-        if (ok) out[m++] = (uint16_t)(mv & 0x0FFF);
+        if (ok) out[(m++) * stride] = (uint16_t)(mv & 0x0FFF);
     }
     return m;
 }
