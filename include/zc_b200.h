@@ -57,6 +57,9 @@ extern "C" {
 #define ZC_POLICY_FIRST 0  /* policy(moves) = moves[0]  : deterministic, used for parity                        */
 #define ZC_POLICY_LAST 1   /* policy(moves) = moves[-1] : deterministic, used for parity                        */
 #define ZC_POLICY_RANDOM 2 /* Policy.random, :10-12 : uniform among untried moves, device RNG                   */
+#define ZC_POLICY_IMMEDIATE_VALUE 3 /* Policy.immediate_value, :14-17 : uniform among the untried moves whose capture value
+                                     * move[1] is >= (best untried value - policy_freedom), device RNG.  Connect Four
+                                     * moves all carry value 0 (c4_backend.py:50), so there it equals ZC_POLICY_RANDOM. */
 
 /* ---- packed root states ---------------------------------------------------------------- */
 
@@ -235,6 +238,9 @@ int zc_search_advance(zc_search *h, void *dev_states, const uint8_t *dev_active,
 
 /* state_to_tensor for many packed states at once (host buffers): out[n][C][H][W] float32 */
 int zc_states_to_tensor(int game, const void *states, int n, float *out);
+
+/* `policy_freedom` of Policy.immediate_value (policy_functions.py:16, the YAML key policy.policy_freedom); default 0 */
+int zc_search_set_policy_freedom(zc_search *h, double policy_freedom);
 
 /* ---- value-network evaluator: the whole residual tower as one fused kernel --------------------
  * Replaces the forward of engine/value_functions.py:78-99 (_batch_worker: model(batch)) over

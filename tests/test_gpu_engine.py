@@ -188,3 +188,16 @@ def test_device_selfplay_refill_and_network():
     x, y = out["dataset"]
     assert x.shape[1:] == (2, 6, 7) and len(x) == len(y) == sum(len(t) for t in out["trajectories"])
     assert out["games_per_hour"] > 0
+
+
+def test_engine_with_immediate_value_policy_on_device():
+    """`policy_functions: immediate_value` (the key engine.py:27 actually reads) + policy.policy_freedom run on the GPU"""
+    eng = Engine({"game": "chess", "backend": "chess_backend", "value_function": "crude_chess_score", "threads": 3,
+                  "policy_functions": "immediate_value", "policy": {"policy_freedom": 3}, "mcts": {"simulations": 64, "c_puct": 1.4}})
+    assert eng.policy.name == "immediate_value" and eng.policy.device_freedom == 3.0
+    res = eng.play_mcts_parallel([0, 1, 2], 64, 1.4)
+    assert set(res) == {0, 1, 2} and all(r is None for r in res.values())
+    assert all(eng.get_state(i).turn == 1 for i in range(3))
+    c4 = Engine({"game": "connect4", "backend": "c4_backend", "value_function": "c4_terminal", "threads": 2,
+                 "policy_functions": "immediate_value"})
+    assert c4.play_mcts(0, 64, 1.4) is None      # all Connect Four moves carry value 0: same as random

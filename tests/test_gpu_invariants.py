@@ -64,3 +64,37 @@ def test_chess_full_size_2048_trees_1600_sims(policy):
     ts.set_roots(chess_roots_set_b(n))
     ts.run(sims, 1.4, 32, _ffi.EVAL_CHESS_CRUDE, policy, seed=5)
     check_sampled(ts, n, sims, 1000.0, sample=12)
+
+
+@pytest.mark.parametrize("freedom", [0.0, 3.0])
+def test_chess_immediate_value_policy_expansion_order(freedom):
+    """Policy.immediate_value (policy_functions.py:14-17): every expansion picks among the untried moves whose
+    capture value is >= best untried - policy_freedom.  So after n < k expansions of the root, every expanded
+    move is worth at least (best unexpanded - freedom); with freedom 0 the expanded set is a top-n by value."""
+    import ctypes as C
+    from zeroclone_b200.games.chess import chess_backend as cb
+    fen = "r3k2r/p1ppqpb1/bn2pnp1/3PN3/1p2P3/2N2Q1p/PPPBBPPP/R3K2R w KQkq - 0 1"      # Kiwipete: 8 captures of 3 kinds
+    root = cb.state_from_fen(fen)
+    n = 64
+    roots = np.zeros(n, dtype=_ffi.CHESS_STATE_DTYPE)
+    for i in range(n):
+        roots[i] = cb.pack_state(root)
+    seen_sets = set()
+    for sims in (5, 12, 30):
+        ts = TreeSearch(_ffi.GAME_CHESS, n, sims)
+        ts.set_roots(roots)
+        ts.set_policy_freedom(freedom)
+        ts.run(sims, 1.4, 32, _ffi.EVAL_CHESS_CRUDE, _ffi.POLICY_IMMEDIATE_VALUE, seed=17)
+        out = ts.results()
+        for t in range(n):
+            k = int(out["result"][t]["n_moves"])
+            vals = out["moves"][t]["value"][:k]
+            expanded = out["visits"][t][:k] > 0
+            assert int(expanded.sum()) == min(sims, k)
+            if expanded.all():
+                continue
+            assert vals[expanded].min() >= vals[~expanded].max() - freedom, (sims, t)
+            seen_sets.add((sims, tuple(np.nonzero(expanded)[0].tolist())))
+        if sims == 30:
+            check_sampled(ts, n, sims, 1000.0, sample=4)
+    assert len(seen_sets) > 10, "trees of one position must not all expand the same moves (device RNG per tree)"

@@ -11,7 +11,7 @@ LIB_PATH = os.path.join(_HERE, "libzc_b200.so")
 
 GAME_C4, GAME_CHESS = 0, 1
 EVAL_C4_TERMINAL, EVAL_C4_POSITIONAL, EVAL_CHESS_CRUDE, EVAL_EXTERNAL, EVAL_C4_ROLLOUT = 0, 1, 2, 3, 4
-POLICY_FIRST, POLICY_LAST, POLICY_RANDOM = 0, 1, 2
+POLICY_FIRST, POLICY_LAST, POLICY_RANDOM, POLICY_IMMEDIATE_VALUE = 0, 1, 2, 3
 ZC_OK, ZC_EINVAL, ZC_ENODEVICE, ZC_ECUDA, ZC_ECAPACITY, ZC_ESTATE = 0, -1, -2, -3, -4, -5
 MAX_MOVES = 256
 RESULT_ONGOING = 2
@@ -81,6 +81,7 @@ def lib() -> C.CDLL:
     L.zc_search_set_roots.argtypes = [vp, vp, i32, vp]
     L.zc_search_set_roots_dev.argtypes = [vp, vp, i32, vp]
     L.zc_search_run.argtypes = [vp, i32, dbl, i32, i32, i32, u64, vp]
+    L.zc_search_set_policy_freedom.argtypes = [vp, dbl]
     L.zc_search_begin.argtypes = [vp, i32, dbl, i32, i32, u64]
     L.zc_search_pending.argtypes = [vp]
     L.zc_search_select.argtypes = [vp, vp, i32, vp]

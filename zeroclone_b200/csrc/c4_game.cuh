@@ -9,6 +9,8 @@ namespace zc {
 struct C4Game {
     static constexpr int kMinBlocks = 7;   // resident 128-thread blocks per SM the fused search is compiled for
     using State = c4::State;
+    // never reached: the host maps immediate_value to random for Connect Four (all move values are 0)
+    ZC_D static int immediate_value_order(const uint4*, const State&, int, int, int, int j, float, uint64_t, int) { return j; }
     static constexpr int SS = 1;            // state slots per node
     static constexpr int FIRST_SLOTS = 9;   // header + state + up to 7 edges: the whole node in one warp load
     static constexpr int PLANE_ELEMS = 84;  // 2 x 6 x 7 (c4_backend.py:52-61)

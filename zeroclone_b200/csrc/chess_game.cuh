@@ -68,6 +68,55 @@ struct ChessGame {
         const uint16_t m = move_at(pnode, pk, ei);
         return chess::play(parent, pmisc, chess::move_from(m), chess::move_to(m), cmisc);
     }
+    // Policy.immediate_value (policy_functions.py:14-17) as mcts.cpp:65-78 applies it: every expansion of a node
+    // picks uniformly among its untried moves whose capture value move[1] is >= (best untried value - freedom).
+    // Which move the t-th expansion of a node picks is a function of the node (its key seeds the draws), so the
+    // warp replays picks 0 .. nexp+m-1 (lane L owns moves L, L+32, ...) and lane j receives the move of
+    // expansion nexp + j.  Called by the whole warp.
+    ZC_D static int immediate_value_order(const uint4* node, const State& st, int k, int nexp, int m, int j, float freedom,
+                                          uint64_t key, int lane) {
+        constexpr int Q = (ZC_MAX_MOVES + 31) / 32;
+        int val[Q];
+        uint32_t untried = 0;                       // bit q: move lane + 32q exists and has not been picked
+#pragma unroll
+        for (int q = 0; q < Q; ++q) {
+            const int i = lane + 32 * q;
+            val[q] = -1;
+            if (i < k) {
+                val[q] = chess::capture_value(chess::piece_at(st, chess::move_to(move_at(node, k, i))));
+                untried |= 1u << q;
+            }
+        }
+        int mine = 0;
+        for (int t = 0; t < nexp + m; ++t) {
+            int best = -1;
+#pragma unroll
+            for (int q = 0; q < Q; ++q)
+                if (untried >> q & 1u) best = max(best, val[q]);
+#pragma unroll
+            for (int d = 16; d >= 1; d >>= 1) best = max(best, __shfl_xor_sync(FULL_MASK, best, d));
+            const float threshold = (float)best - freedom;
+            uint32_t cand = 0;
+#pragma unroll
+            for (int q = 0; q < Q; ++q)
+                if ((untried >> q & 1u) && (float)val[q] >= threshold) cand |= 1u << q;
+            int total;
+            const int before = warp_excl_scan(__popc(cand), lane, total);
+            const int r = (int)(rng_mix(key ^ (0x9E3779B97F4A7C15ull * (uint64_t)(t + 1))) % (uint64_t)max(total, 1));
+            int pick = -1;
+            if (r >= before && r < before + __popc(cand)) {
+                uint32_t c = cand;
+                for (int s = r - before; s > 0; --s) c &= c - 1;     // the (r - before)-th candidate of this lane
+                const int q = __ffs((int)c) - 1;
+                untried &= ~(1u << q);
+                pick = lane + 32 * q;
+            }
+            const unsigned who = __ballot_sync(FULL_MASK, pick >= 0);
+            const int chosen = __shfl_sync(FULL_MASK, pick, who ? __ffs((int)who) - 1 : 0);
+            if (t - nexp == j) mine = chosen;
+        }
+        return mine;
+    }
     ZC_HD static int count_moves(Ctx& gx, const State& s, uint32_t misc) {
         return chess::generate(s, (int)(misc & chess::MISC_TURN), gx.moves, gx.stride);
     }

@@ -39,6 +39,7 @@ struct SearchParams {
     int batch_size;          // 1..32
     int evaluator;
     int policy;
+    float policy_freedom;    // Policy.immediate_value only
     double c;
     uint64_t seed;
     // split-phase leaf packing
@@ -355,8 +356,10 @@ ZC_D bool expand_stepwise(const SearchParams& p, typename G::Ctx& gx, uint4* __r
         int ei = 0x7FFFFFFF, ck = 0;
         typename G::State cs = Pst;
         uint32_t cmisc = 0;
+        int ei_iv = 0;
+        if (p.policy == 3) ei_iv = G::immediate_value_order(arena + P, Pst, Pk, Pnexp, m, j, p.policy_freedom, nkey, lane);
         if (act) {
-            ei = expansion_order(p.policy, Pk, Pnexp + j, nkey);
+            ei = p.policy == 3 ? ei_iv : expansion_order(p.policy, Pk, Pnexp + j, nkey);
             cs = G::child(Pst, Pmisc, arena + P, Pk, ei, cmisc);
             ck = G::count_moves(gx, cs, cmisc);
         }

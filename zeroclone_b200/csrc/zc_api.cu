@@ -70,6 +70,7 @@ struct zc_search {
     int sp_left = 0, sp_batch = 0, sp_policy = 0, sp_selected = 0;
     double sp_c = 1.4;
     uint64_t sp_seed = 0;
+    double policy_freedom = 0.0;   // Policy.immediate_value
 };
 
 // ------------------------------------------------------------------------------- C4 move order
@@ -440,7 +441,9 @@ static SearchParams make_params(zc_search* h, int sims, double c, int batch, int
     p.simulations = sims;
     p.batch_size = batch;
     p.evaluator = evaluator;
-    p.policy = policy;
+    // Connect Four moves all carry value 0 (c4_backend.py:50): immediate_value picks uniformly = random
+    p.policy = (policy == ZC_POLICY_IMMEDIATE_VALUE && h->game == ZC_GAME_C4) ? ZC_POLICY_RANDOM : policy;
+    p.policy_freedom = (float)h->policy_freedom;
     p.c = c;
     p.seed = seed;
     p.scratch = h->scratch;
@@ -451,7 +454,7 @@ static int check_search_args(zc_search* h, int sims, int batch, int policy) {
     if (h->n_trees < 1) return fail(ZC_ESTATE, "no roots set");
     if (sims < 0 || sims > h->max_sims) return fail(ZC_EINVAL, "simulations exceeds max_sims of the handle");
     if (batch < 1 || batch > 32) return fail(ZC_EINVAL, "batch_size must be in 1..32");
-    if (policy != ZC_POLICY_FIRST && policy != ZC_POLICY_LAST && policy != ZC_POLICY_RANDOM)
+    if (policy != ZC_POLICY_FIRST && policy != ZC_POLICY_LAST && policy != ZC_POLICY_RANDOM && policy != ZC_POLICY_IMMEDIATE_VALUE)
         return fail(ZC_EINVAL, "unsupported policy");
     return ZC_OK;
 }
@@ -472,6 +475,13 @@ extern "C" int zc_search_run(zc_search* h, int simulations, double c, int batch_
     ZC_DISPATCH(h->game, k_search_fused<G><<<grid, SEARCH_BLOCK, 0, st>>>(p));
     h->launches++;
     CUDA_TRY(cudaGetLastError());
+    return ZC_OK;
+}
+
+extern "C" int zc_search_set_policy_freedom(zc_search* h, double policy_freedom) {
+    if (int rc = check_handle(h)) return rc;
+    if (!(policy_freedom >= 0.0)) return fail(ZC_EINVAL, "policy_freedom must be >= 0");
+    h->policy_freedom = policy_freedom;
     return ZC_OK;
 }
 

@@ -64,6 +64,7 @@ def search_batch(states: Sequence, value, policy, backend, simulations: int, c: 
         seed = int(np.random.SeedSequence().generate_state(1, dtype=np.uint64)[0])
     ts = searcher(game, n, simulations)
     ts.set_roots(roots)
+    ts.set_policy_freedom(getattr(policy, "device_freedom", 0.0))
     if kind == "builtin":
         ts.run(simulations, c, batch_size, ev, pol, seed)
     else:

@@ -9,7 +9,8 @@ from . import _ffi
 
 
 class Policy:
-    DEVICE = {"random": _ffi.POLICY_RANDOM, "first": _ffi.POLICY_FIRST, "last": _ffi.POLICY_LAST}
+    DEVICE = {"random": _ffi.POLICY_RANDOM, "first": _ffi.POLICY_FIRST, "last": _ffi.POLICY_LAST,
+              "immediate_value": _ffi.POLICY_IMMEDIATE_VALUE}
 
     def __init__(self, name=None, **kwargs):
         self.name = name if name is not None else "random"
@@ -28,6 +29,11 @@ class Policy:
         except KeyError:
             raise NotImplementedError(f"policy {self.name!r} has no device implementation (libzc_b200 has no CPU "
                                       "search to fall back to)") from None
+
+    @property
+    def device_freedom(self) -> float:
+        """policy_freedom handed to the device search (immediate_value only)"""
+        return float(self.args.get("policy_freedom", 0))
 
     # host semantics, one move list at a time (policy_functions.py:10-17)
     def random(self, moves, args):

@@ -66,6 +66,10 @@ class TreeSearch:
         check(lib().zc_search_set_roots_dev(self._h, C.c_void_p(dev_ptr), n, _stream_ptr(stream)))
         self.n_trees = n
 
+    def set_policy_freedom(self, policy_freedom: float) -> None:
+        """`policy_freedom` of Policy.immediate_value (policy_functions.py:16)"""
+        check(lib().zc_search_set_policy_freedom(self._h, float(policy_freedom)))
+
     # -- fused search with a built-in evaluator ------------------------------------------------
     def run(self, simulations: int, c: float = 1.4, batch_size: int = 32, evaluator: int = EVAL_C4_TERMINAL,
             policy: int = POLICY_FIRST, seed: int = 0, stream=None) -> None:

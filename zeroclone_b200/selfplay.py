@@ -62,6 +62,7 @@ class DeviceSelfPlay:
         self.device = torch.cuda.current_device() if device is None else device
         self.kind, self.ev = value.device_spec(self.game)
         self.pol = policy.device_policy
+        self.pol_freedom = getattr(policy, "device_freedom", 0.0)
         self.init_rec = self._pack(backend.create_init_state())
 
     def _pack(self, state):
@@ -85,6 +86,7 @@ class DeviceSelfPlay:
             hist_all = torch.zeros((n_slots, 2, self.hist_cap, 8), dtype=torch.uint8, device=dev) if chess else None
             hlen_all = torch.zeros((n_slots, 2), dtype=torch.int32, device=dev) if chess else None
             ts = self._mcts.searcher(self.game, n_slots, simulations, self.device)
+            ts.set_policy_freedom(self.pol_freedom)
             slot_game = list(range(n_slots))              # game id played in each slot
             started, finished = n_slots, 0
             results = [None] * total_games
