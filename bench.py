@@ -251,12 +251,12 @@ def run_ours(args):
     batches = sims_done / BATCH
     tree_bytes_step = sims_done * (node_bytes + 4 + 20) + batches * (depth + 1) * (node_bytes + 2 * 20)
     # measured DRAM traffic per simulation of the tree kernels: dram__bytes_read+write of one `ncu --set full`
-    # capture of k_search_fused divided by the simulations of that launch (profiles/r1b_k_search_fused_*_ncu.txt)
-    ncu_bytes_per_sim = 528.0 if chess else 148.0
+    # capture of k_search_fused divided by the simulations of that launch (profiles/r1d_k_search_fused_chess_ncu.txt, r1b_k_search_fused_c4_ncu.txt)
+    ncu_bytes_per_sim = 589.0 if chess else 148.0
     roofline_tree = {"bound": "hbm", "achieved": tree_bytes_step * args.steps / (tree_ms * 1e-3) / 1e9 if tree_ms else None,
                      "peak": hbm_peak, "unit": "GB/s",
                      "traffic": None if use_net else ncu_bytes_per_sim * sims_done,
-                     "traffic_source": "ncu capture of the same kernel at 8192/2048 trees, scaled per simulation", "launches": n_tree,
+                     "traffic_source": "ncu capture of the same kernel (c4 8192 trees, chess 16384 trees x 800 sims), scaled per simulation", "launches": n_tree,
                      "avg_launch_ms": tree_ms / max(1, n_tree), "share_of_step": tree_ms / ms}
     if roofline_tree["achieved"]:
         roofline_tree["frac"] = roofline_tree["achieved"] / hbm_peak

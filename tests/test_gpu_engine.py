@@ -192,6 +192,7 @@ def test_device_selfplay_refill_and_network():
 
 def test_engine_with_immediate_value_policy_on_device():
     """`policy_functions: immediate_value` (the key engine.py:27 actually reads) + policy.policy_freedom run on the GPU"""
+    from engine.engine import Engine
     eng = Engine({"game": "chess", "backend": "chess_backend", "value_function": "crude_chess_score", "threads": 3,
                   "policy_functions": "immediate_value", "policy": {"policy_freedom": 3}, "mcts": {"simulations": 64, "c_puct": 1.4}})
     assert eng.policy.name == "immediate_value" and eng.policy.device_freedom == 3.0
