@@ -1,7 +1,7 @@
 """Ad-hoc: accuracy + speed of the value-net forward variants on the GPU (development aid)."""
 import sys, time
 import torch
-from zeroclone_b200.evaluator import NetEvaluator, tower_flops_per_leaf
+from zeroclone_b200.evaluator import TorchTowerEvaluator as NetEvaluator, tower_flops_per_leaf
 from zeroclone_b200.models.connect4_value.network import ValueNetwork
 
 torch.backends.cudnn.benchmark = True

@@ -2,7 +2,7 @@
 import sys
 import torch
 import torch.nn.functional as F
-from zeroclone_b200.evaluator import NetEvaluator, tower_flops_per_leaf, _fold
+from zeroclone_b200.evaluator import TorchTowerEvaluator as NetEvaluator, tower_flops_per_leaf, _fold
 from zeroclone_b200.models.connect4_value.network import ValueNetwork
 
 torch.backends.cudnn.benchmark = True

@@ -1,7 +1,7 @@
 """Development aid: fused tower kernel vs the PyTorch paths (accuracy + speed) on the GPU."""
 import sys
 import torch
-from zeroclone_b200.evaluator import FusedTowerEvaluator, NetEvaluator, tower_flops_per_leaf
+from zeroclone_b200.evaluator import FusedTowerEvaluator, TorchTowerEvaluator, tower_flops_per_leaf
 
 game = sys.argv[1] if len(sys.argv) > 1 else "c4"
 B = int(sys.argv[2]) if len(sys.argv) > 2 else 131072
@@ -27,7 +27,7 @@ with torch.no_grad():
     ref = model(x[:nref]).view(-1)
 xd = x.to("cuda", torch.bfloat16).contiguous()
 fused = FusedTowerEvaluator(model, "cuda")
-cud = NetEvaluator(model, "cuda", torch.bfloat16)
+cud = TorchTowerEvaluator(model, "cuda", torch.bfloat16)
 for n in (1, 2, 3, 4, 7, 300, nref):
     got = fused(xd[:n]).cpu()
     torch.cuda.synchronize()
