@@ -289,6 +289,8 @@ def run_ours(args):
         "tree_stats": {"mean_leaf_depth": depth, "nodes_per_tree": cnt["nodes"] / trees, "mean_node_bytes": node_bytes,
                        "algorithmic_bytes_per_sim": tree_bytes_step / sims_done},
     }
+    if args.selfplay_games < 0:     # enough games in flight to occupy the GPU, few enough to finish in seconds
+        args.selfplay_games = {"c4_value_net": 2048, "c4_heuristic": 16384, "chess_crude": 4096, "chess_value_net": 512}[args.workload]
     if args.selfplay_games > 0:
         # secondary half of the metric: self-play games/hour with the full move loop on the device
         # (search, apply move, win/draw detection, refill); not part of the timed steps above
@@ -491,7 +493,8 @@ def main():
     ap.add_argument("--trees", type=int, default=0, help="trees per GPU (default: the workload's)")
     ap.add_argument("--sims", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--selfplay-games", type=int, default=512, help="games of the games/hour side measurement (0 = skip)")
+    ap.add_argument("--selfplay-games", type=int, default=-1,
+                    help="games (all in flight at once) of the games/hour side measurement; 0 = skip, -1 = per-workload default")
     ap.add_argument("--cpu-budget", type=float, default=15.0)
     args = ap.parse_args()
     if args.impl == "reference":
