@@ -65,7 +65,6 @@ struct Params {
     int n_leaves;
     int n_layers;                  // 1 + 2*blocks
     unsigned int* fault;           // set when a barrier wait times out
-    int dbg;                       // timing experiments only (ZC_TOWER_DEBUG): results are wrong when non-zero
 };
 
 // ------------------------------------------------------------------------------------ PTX helpers
@@ -269,7 +268,6 @@ __global__ void __launch_bounds__(N_THREADS, 1) k_value_tower(const Params p) {
                     for (int tap = 0; tap < 9; ++tap, ++cnt) {
                         const uint32_t st = cnt % NSTAGE, ph = (cnt / NSTAGE) & 1u;
                         mbar_wait(bar_wempty + 8 * st, ph ^ 1u, p.fault, 1);
-                        if ((p.dbg & 4) && cnt >= NSTAGE) { mbar_arrive(bar_wfull + 8 * st); continue; }
                         mbar_expect_tx(bar_wfull + 8 * st, bytes);
                         const uint8_t* src = PAIR ? p.wimg2 + ((size_t)(layer * 9 + tap) * 2 + crank) * STAGE_BYTES
                                                   : p.wimg + (size_t)(layer * 9 + tap) * STAGE_BYTES;
@@ -311,7 +309,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) k_value_tower(const Params p) {
                     // group 2 takes over its dx = 0 accumulator, free when that epilogue is complete, which it
                     // reports through the a_ready of the step after this one.  (Group 0 reuses an accumulator of
                     // the step before the previous one, released long ago.)
-                    if (NT == 2 && n >= 1 && !(p.dbg & 1)) {
+                    if (NT == 2 && n >= 1) {
                         if (g == 1) {
                             const int n0 = n - 1;
                             mbar_wait(bar_pfree + 8 * (n0 % NT), (uint32_t)(n0 / NT) & 1u, p.fault, 3);
@@ -465,7 +463,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) k_value_tower(const Params p) {
                             xreg[slot][cc * 8 + (i >> 1)] = keep ? pk : xr;
                         }
                     }
-                    if (valid && !last && !(p.dbg & 2)) {
+                    if (valid && !last) {
                         const int chunk = half * 8 + cc * 2;
                         *reinterpret_cast<uint4*>(arow + chunk * A_LBO) = make_uint4(o[0], o[1], o[2], o[3]);
                         *reinterpret_cast<uint4*>(arow + (chunk + 1) * A_LBO) = make_uint4(o[4], o[5], o[6], o[7]);

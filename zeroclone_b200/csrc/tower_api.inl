@@ -88,9 +88,7 @@ extern "C" int zc_tower_create(int game, int device, int n_blocks, const float* 
     TOWER_TRY(cudaMemcpy(t->bias, conv_b, sizeof(float) * nl * CH, cudaMemcpyHostToDevice));
     TOWER_TRY(cudaMemcpy(t->head_w, head_w, sizeof(float) * CH, cudaMemcpyHostToDevice));
     TOWER_TRY(cudaMemset(t->fault, 0, sizeof(unsigned int)));
-    TOWER_TRY(cudaFuncSetAttribute(k_value_tower<GeomC4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
     TOWER_TRY(cudaFuncSetAttribute(k_value_tower<GeomC4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
-    TOWER_TRY(cudaFuncSetAttribute(k_value_tower<GeomChess, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
     TOWER_TRY(cudaFuncSetAttribute(k_value_tower<GeomChess, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
 #undef TOWER_TRY
     *out = t;
@@ -125,11 +123,9 @@ extern "C" int zc_tower_forward(zc_tower* t, const void* dev_planes_bf16, int n_
     p.n_leaves = n_leaves;
     p.n_layers = t->n_layers;
     p.fault = t->fault;
-    p.dbg = getenv("ZC_TOWER_DEBUG") ? atoi(getenv("ZC_TOWER_DEBUG")) : 0;
     const int nb = t->game == ZC_GAME_C4 ? GeomC4::NB : GeomChess::NB;
     const int n_groups = (n_leaves + nb - 1) / nb;
-    const bool pair = getenv("ZC_TOWER_PAIR") ? atoi(getenv("ZC_TOWER_PAIR")) != 0 : true;
-    const int csz = pair ? 2 : 1;
+    constexpr int csz = 2;                             // CTA pairs (tcgen05 cta_group::2)
     int grid = std::max(1, std::min(t->n_sms, (n_groups + NT - 1) / NT));
     grid = std::max(csz, grid / csz * csz);            // whole pairs
     cudaStream_t st = (cudaStream_t)stream;
@@ -146,8 +142,7 @@ extern "C" int zc_tower_forward(zc_tower* t, const void* dev_planes_bf16, int n_
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     const bool c4 = t->game == ZC_GAME_C4;
-    void (*kern)(const Params) = pair ? (c4 ? k_value_tower<GeomC4, true> : k_value_tower<GeomChess, true>)
-                                      : (c4 ? k_value_tower<GeomC4, false> : k_value_tower<GeomChess, false>);
+    void (*kern)(const Params) = c4 ? k_value_tower<GeomC4, true> : k_value_tower<GeomChess, true>;
     CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, p));
     ++t->launches;
     return ZC_OK;
