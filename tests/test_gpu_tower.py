@@ -116,3 +116,25 @@ def test_tower_rejects_what_it_cannot_compute():
         ev(torch.zeros(4, *shape, dtype=torch.bfloat16))
     with pytest.raises(ValueError):
         NetEvaluator(model, "cuda", torch.float16)
+
+
+def test_tower_soak_random_batches_bit_identical():
+    """a few thousand launches with random sizes / offsets, other kernels in between: a leaf's value never
+    depends on the batch it is evaluated in (tools/tower_soak.py runs the long version)"""
+    import time
+    model, shape = make_model("c4", True, seed=9)
+    ev = NetEvaluator(model, "cuda")
+    n_all = 20000
+    x = random_planes(n_all, shape, 11).to("cuda", torch.bfloat16)
+    ref = ev(x).clone()
+    g = torch.Generator().manual_seed(1)
+    busy = torch.empty(32 << 20, dtype=torch.uint8, device="cuda")
+    t0, launches = time.time(), 0
+    while time.time() - t0 < 3.0:
+        n = int(torch.randint(1, 40 if launches % 3 == 0 else 3000, (1,), generator=g))
+        off = int(torch.randint(0, n_all - n, (1,), generator=g))
+        if launches % 5 == 0:
+            busy.fill_(launches & 255)
+        assert torch.equal(ev(x[off:off + n].contiguous()), ref[off:off + n]), (launches, n, off)
+        launches += 1
+    assert launches > 500

@@ -107,10 +107,17 @@ class TreeSearch:
         with torch.cuda.device(dev):
             stream = torch.cuda.current_stream().cuda_stream
             self.begin(simulations, c, batch_size, policy, seed)
+            nvtx = torch.cuda.nvtx       # ranges for ncu / timeline filtering; a few ns each
             while self.pending() > 0:
+                nvtx.range_push("zc.select")
                 self.select(self._planes.data_ptr(), code, stream)
+                nvtx.range_pop()
+                nvtx.range_push("zc.evaluate")
                 evaluator(self._planes, out=self._values)
+                nvtx.range_pop()
+                nvtx.range_push("zc.backprop")
                 self.backprop(self._values.data_ptr(), stream)
+                nvtx.range_pop()
 
     # -- readout ---------------------------------------------------------------------------------
     def results(self, stats: bool = True, stream=None, reuse: bool = False) -> dict:
