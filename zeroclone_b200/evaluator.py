@@ -5,8 +5,8 @@ evaluation is ONE forward per search batch.
 
 `NetEvaluator` (= FusedTowerEvaluator) is the product path: the whole tower as one hand-written
 sm_100a kernel (csrc/tower.cuh) behind the C-ABI (zc_tower_*).  `TorchTowerEvaluator` is the same
-network through PyTorch/cuDNN; it exists for A/B timing, for tests, and for the fp16 / fp32 plane
-dtypes the kernel does not compute in.  BatchNorm (eval mode, network.py:15,18,30) is folded into
+network through PyTorch/cuDNN; nothing in the package calls it -- it exists for A/B timing (tools/) and
+as a second opinion in tests.  BatchNorm (eval mode, network.py:15,18,30) is folded into
 the convolution weights in fp32 before the cast to the compute dtype in both.
 """
 from __future__ import annotations

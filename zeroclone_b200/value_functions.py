@@ -65,14 +65,13 @@ class Value:
     def evaluator(self):
         if self._net is None:
             import torch
-            from .evaluator import NetEvaluator, TorchTowerEvaluator
+            from .evaluator import NetEvaluator
             if not torch.cuda.is_available():
                 raise RuntimeError("the neural evaluator runs on the GPU only (no CPU fallback)")
-            dtype = {"bf16": torch.bfloat16, "fp16": torch.float16, "fp32": torch.float32}[self.init_args.get("dtype", "bf16")]
+            if self.init_args.get("dtype", "bf16") != "bf16":
+                raise ValueError("the neural evaluator is the fused sm_100a tower kernel: bf16 operands, fp32 accumulation")
             dev = torch.device("cuda", self.init_args.get("device", torch.cuda.current_device()))
-            # bf16 (the default) is the fused sm_100a tower kernel; fp16 / fp32 are explicit requests for the
-            # PyTorch reference forward
-            self._net = NetEvaluator(self.model, dev) if dtype == torch.bfloat16 else TorchTowerEvaluator(self.model, dev, dtype)
+            self._net = NetEvaluator(self.model, dev)
         return self._net
 
     # ------------------------------------------------------------------ heuristics (host, per state)
