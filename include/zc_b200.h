@@ -210,6 +210,10 @@ int zc_chess_to_tensor(const zc_chess_state *s, float *out /* [17][8][8] */); /*
  * (the stalemate branch of check_draw), bit 2 = side to move in check. */
 int zc_chess_legal_moves_batch(int device, const zc_chess_state *states, int n, zc_chess_move *moves,
                                int32_t *counts, int32_t *flags);
+/* the same through the warp-cooperative generator (one position per warp, one piece per lane) that the
+ * search uses when a single node needs its move list */
+int zc_chess_legal_moves_batch_warp(int device, const zc_chess_state *states, int n, zc_chess_move *moves,
+                                    int32_t *counts, int32_t *flags);
 /* perft as the reference's rules count it (number of legal moves at the last ply), breadth-first
  * on the device */
 int zc_chess_perft(int device, const zc_chess_state *root, int depth, uint64_t *out);

@@ -35,13 +35,15 @@ def states_array(items):
     return arr
 
 
-def device_legal(arr):
+def device_legal(arr, warp=False):
+    """warp=False: one thread per position (generate); True: one warp per position (generate_warp)"""
     n = len(arr)
     moves = np.zeros((n, _ffi.MAX_MOVES), dtype=_ffi.CHESS_MOVE_DTYPE)
     counts = np.zeros(n, dtype=np.int32)
     flags = np.zeros(n, dtype=np.int32)
-    _ffi.check(_ffi.lib().zc_chess_legal_moves_batch(0, arr.ctypes.data_as(C.c_void_p), n, moves.ctypes.data_as(C.c_void_p),
-                                                     counts.ctypes.data_as(C.c_void_p), flags.ctypes.data_as(C.c_void_p)))
+    fn = _ffi.lib().zc_chess_legal_moves_batch_warp if warp else _ffi.lib().zc_chess_legal_moves_batch
+    _ffi.check(fn(0, arr.ctypes.data_as(C.c_void_p), n, moves.ctypes.data_as(C.c_void_p),
+                  counts.ctypes.data_as(C.c_void_p), flags.ctypes.data_as(C.c_void_p)))
     return moves, counts, flags
 
 
@@ -49,10 +51,11 @@ def as_lists(moves, k):
     return [[int(m["fr"]), int(m["fc"]), int(m["tr"]), int(m["tc"]), float(m["value"])] for m in moves[:k]]
 
 
-def test_device_movegen_matches_reference_playouts():
+@pytest.mark.parametrize("warp", [False, True])
+def test_device_movegen_matches_reference_playouts(warp):
     g = load_golden("chess_rules.json.gz")
     recs = [r for trace in g["playouts"] for r in trace] + list(g["fens"].values())
-    moves, counts, flags = device_legal(states_array(recs))
+    moves, counts, flags = device_legal(states_array(recs), warp)
     for i, rec in enumerate(recs):
         assert as_lists(moves[i], counts[i]) == rec["legal"], i
         assert bool(flags[i] & 1) == rec["win"], i
@@ -60,10 +63,11 @@ def test_device_movegen_matches_reference_playouts():
             assert flags[i] & 2
 
 
-def test_device_movegen_matches_oracle_on_random_positions():
+@pytest.mark.parametrize("warp", [False, True])
+def test_device_movegen_matches_oracle_on_random_positions(warp):
     rng = np.random.default_rng(23)
     states = []
-    for g in range(40):
+    for g in range(40 if not warp else 120):
         s = zo.ch_init()
         for ply in range(int(rng.integers(0, 140))):
             mv = zo.ch_legal(s)
@@ -71,7 +75,7 @@ def test_device_movegen_matches_oracle_on_random_positions():
                 break
             s = zo.ch_play(s, mv[int(rng.integers(len(mv)))])
             states.append(s)
-    moves, counts, flags = device_legal(states_array(states))
+    moves, counts, flags = device_legal(states_array(states), warp)
     for i, s in enumerate(states):
         assert as_lists(moves[i], counts[i]) == [list(m[0]) + [m[1]] for m in zo.ch_legal(s)], i
         assert bool(flags[i] & 1) == zo.ch_check_win(s)

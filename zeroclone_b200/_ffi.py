@@ -101,6 +101,7 @@ def lib() -> C.CDLL:
     L.zc_chess_check_draw.argtypes = [vp, vp, i32, vp, i32]
     L.zc_chess_to_tensor.argtypes = [vp, vp]
     L.zc_chess_legal_moves_batch.argtypes = [i32, vp, i32, vp, vp, vp]
+    L.zc_chess_legal_moves_batch_warp.argtypes = [i32, vp, i32, vp, vp, vp]
     L.zc_chess_perft.argtypes = [i32, vp, i32, vp]
     L.zc_c4_rules_batch.argtypes = [i32, vp, i32, vp, vp]
     L.zc_search_advance.argtypes = [vp, vp, vp, vp, vp, i32, vp, vp, vp]

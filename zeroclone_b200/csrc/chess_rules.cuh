@@ -303,6 +303,104 @@ ZC_HD int generate(const Board& b, int turn, uint16_t* out, int stride = 1) {
     return m;
 }
 
+#ifdef __CUDACC__
+// The same list as generate(), produced by a whole warp for ONE position: lane r owns the side to move's
+// r-th piece in square order (the order the reference scans, chess_backend.cpp:203), builds that piece's
+// targets as up to eight ordered segments (one per direction for sliders and the king -- queen_dirs /
+// king_dirs order; one ascending mask for a knight; the four pawn moves in their fixed order), filters
+// them with the same legality rule as generate(), and an exclusive scan of the per-piece counts places
+// every piece's moves.  All lanes must call it with the same arguments; out[i * stride] receives move i.
+__device__ __forceinline__ int generate_warp(const Board& b, int turn, uint16_t* out, int stride, int lane) {
+    if (insufficient_material(b)) return 0;
+    const Sets s = derive(b, turn);
+    if (zc_popc64(s.own) > 32) {                       // more pieces than lanes (only a contrived FEN): one lane does it
+        int n = 0;
+        if (lane == 0) n = generate(b, turn, out, stride);
+        return __shfl_sync(0xFFFFFFFFu, n, 0);
+    }
+    const uint64_t empty = ~s.occ;
+    const uint64_t targets_ok = ~s.own & ~s.e_king;
+    const bool has_king = s.own_king != 0;
+    const int ksq = has_king ? zc_ctz64(s.own_king) : 0;
+    uint64_t pinned = 0;
+    const bool checked = has_king && king_danger(turn, ksq, s.occ, s.own, s.e_pawn, s.e_knight, s.e_bishop | s.e_queen,
+                                                 s.e_rook | s.e_queen, s.e_king, pinned);
+    uint64_t seg[8];
+#pragma unroll
+    for (int d = 0; d < 8; ++d) seg[d] = 0;
+    uint32_t asc = 0xACu;                              // bit d: segment d is emitted in ascending square order (dirs 2,3,5,7)
+    int sq = 0;
+    bool king_piece = false;
+    const bool mine = lane < zc_popc64(s.own);
+    if (mine) {
+        uint64_t m = s.own;
+        for (int i = 0; i < lane; ++i) m &= m - 1;
+        sq = zc_ctz64(m);
+        const int type = piece_at(b, sq) & 7, r = sq >> 3, c = sq & 7;
+        if (type == PAWN) {                            // single push, double push, capture dc=-1, capture dc=+1
+            const int dir = turn == 0 ? -1 : 1, home = turn == 0 ? 6 : 1;
+            const int nr = r + dir;
+            if (nr >= 0 && nr < 8) {
+                const int one = nr * 8 + c;
+                if (empty >> one & 1) {
+                    seg[0] = bit(one);
+                    const int two = one + dir * 8;
+                    if (r == home && (empty >> two & 1)) seg[1] = bit(two);
+                }
+                const uint64_t capturable = s.enemy & ~s.e_king;
+                if (c > 0 && (capturable >> (one - 1) & 1)) seg[2] = bit(one - 1);
+                if (c < 7 && (capturable >> (one + 1) & 1)) seg[3] = bit(one + 1);
+            }
+        } else if (type == KNIGHT) {
+            seg[0] = knight_targets(sq) & targets_ok;
+            asc = 1u;
+        } else if (type != 0) {                        // king, bishop, rook, queen: per direction, outward
+            uint64_t rr[8];
+            rays_of<0, 8>(sq, rr);
+            king_piece = type == KING;
+            const uint64_t reach = king_piece ? king_targets(sq) : ~0ull;
+            const bool diag = type != ROOK, orth = type != BISHOP;
+#pragma unroll
+            for (int d = 0; d < 8; ++d)
+                if (d < 4 ? diag : orth) seg[d] = ray_until_blocker(d, rr[d], s.occ) & targets_ok & reach;
+        }
+        if (has_king && (checked || king_piece || (pinned >> sq & 1))) {   // the reference's make-move test (:345-358)
+#pragma unroll
+            for (int d = 0; d < 8; ++d) {
+                uint64_t tg = seg[d];
+                while (tg) {
+                    const int t = zc_ctz64(tg);
+                    tg &= tg - 1;
+                    if (!move_keeps_king_safe(s, turn, sq, t, king_piece)) seg[d] &= ~bit(t);
+                }
+            }
+        }
+    }
+    int cnt = 0;
+#pragma unroll
+    for (int d = 0; d < 8; ++d) cnt += zc_popc64(seg[d]);
+    int x = cnt;                                       // exclusive scan over lanes = over pieces in square order
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int y = __shfl_up_sync(0xFFFFFFFFu, x, d);
+        if (lane >= d) x += y;
+    }
+    const int total = __shfl_sync(0xFFFFFFFFu, x, 31);
+    int pos = x - cnt;
+#pragma unroll
+    for (int d = 0; d < 8; ++d) {
+        uint64_t tg = seg[d];
+        while (tg) {
+            const int t = (asc >> d & 1u) ? zc_ctz64(tg) : 63 - zc_clz64(tg);
+            tg &= ~bit(t);
+            out[(size_t)(pos++) * stride] = pack_move(sq, t);
+        }
+    }
+    __syncwarp();
+    return total;
+}
+#endif
+
 // chess_backend.cpp:364-400 on the board planes; flags in/out through `misc`.
 ZC_HD Board play(const Board& b, uint32_t misc, int from, int to, uint32_t& misc_out) {
     Board n = b;

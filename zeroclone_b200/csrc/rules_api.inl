@@ -217,6 +217,24 @@ __global__ void k_chess_legal_batch(const zc_chess_state* __restrict__ states, i
     flags[t] = (k == 0 && chk ? 1 : 0) | (k == 0 && !chk ? 2 : 0) | (chk ? 4 : 0);
 }
 
+// the warp-cooperative generator (one position per warp) behind the same outputs
+__global__ void k_chess_legal_batch_warp(const zc_chess_state* __restrict__ states, int n, zc_chess_move* __restrict__ moves,
+                                         int32_t* __restrict__ counts, int32_t* __restrict__ flags, uint16_t* __restrict__ scratch) {
+    const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (t >= n) return;
+    const zc_chess_state s = states[t];
+    const chess::Board b = board_of(s);
+    const int turn = s.turn ? 1 : 0;
+    uint16_t* mv = scratch + (size_t)t * ChessGame::MOVE_SCRATCH;
+    const int k = chess::generate_warp(b, turn, mv, 1, lane);
+    for (int i = lane; i < k; i += 32) moves[(size_t)t * ZC_MAX_MOVES + i] = decode_move(b, mv[i]);
+    if (lane == 0) {
+        counts[t] = k;
+        const bool chk = chess::in_check(b, turn);
+        flags[t] = (k == 0 && chk ? 1 : 0) | (k == 0 && !chk ? 2 : 0) | (chk ? 4 : 0);
+    }
+}
+
 __global__ void k_perft_count(const PerftState* __restrict__ frontier, unsigned long long n,
                               unsigned long long* __restrict__ total) {
     const unsigned long long t = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -260,8 +278,18 @@ struct DevBuf {   // frees on scope exit
     ~DevBuf() { cudaFree(p); }
 };
 
+static int chess_legal_moves_batch(int device, const zc_chess_state* states, int n, zc_chess_move* moves, int32_t* counts,
+                                   int32_t* flags, bool warp_cooperative);
 extern "C" int zc_chess_legal_moves_batch(int device, const zc_chess_state* states, int n, zc_chess_move* moves,
                                           int32_t* counts, int32_t* flags) {
+    return chess_legal_moves_batch(device, states, n, moves, counts, flags, false);
+}
+extern "C" int zc_chess_legal_moves_batch_warp(int device, const zc_chess_state* states, int n, zc_chess_move* moves,
+                                               int32_t* counts, int32_t* flags) {
+    return chess_legal_moves_batch(device, states, n, moves, counts, flags, true);
+}
+static int chess_legal_moves_batch(int device, const zc_chess_state* states, int n, zc_chess_move* moves, int32_t* counts,
+                                   int32_t* flags, bool warp_cooperative) {
     if (!states || !moves || !counts || !flags || n < 1) return fail(ZC_EINVAL, "bad argument");
     if (int rc = use_device(device)) return rc;
     DevBuf ds, dm, dc, df, dscr;
@@ -272,8 +300,12 @@ extern "C" int zc_chess_legal_moves_batch(int device, const zc_chess_state* stat
     CUDA_TRY(cudaMalloc(&dscr.p, sizeof(uint16_t) * (size_t)n * ChessGame::MOVE_SCRATCH));
     CUDA_TRY(cudaMemcpy(ds.p, states, sizeof(zc_chess_state) * (size_t)n, cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMemset(dm.p, 0, sizeof(zc_chess_move) * (size_t)n * ZC_MAX_MOVES));
-    k_chess_legal_batch<<<(n + 63) / 64, 64>>>((const zc_chess_state*)ds.p, n, (zc_chess_move*)dm.p, (int32_t*)dc.p,
-                                               (int32_t*)df.p, (uint16_t*)dscr.p);
+    if (warp_cooperative)
+        k_chess_legal_batch_warp<<<(n + 3) / 4, 128>>>((const zc_chess_state*)ds.p, n, (zc_chess_move*)dm.p, (int32_t*)dc.p,
+                                                       (int32_t*)df.p, (uint16_t*)dscr.p);
+    else
+        k_chess_legal_batch<<<(n + 63) / 64, 64>>>((const zc_chess_state*)ds.p, n, (zc_chess_move*)dm.p, (int32_t*)dc.p,
+                                                   (int32_t*)df.p, (uint16_t*)dscr.p);
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaMemcpy(moves, dm.p, sizeof(zc_chess_move) * (size_t)n * ZC_MAX_MOVES, cudaMemcpyDeviceToHost));
     CUDA_TRY(cudaMemcpy(counts, dc.p, sizeof(int32_t) * (size_t)n, cudaMemcpyDeviceToHost));
