@@ -51,6 +51,7 @@ struct C4Game {
         return c4::play(parent, c4::move_col(c4::legal_mask(parent), ei));
     }
     ZC_HD static int count_moves(Ctx&, const State& s, uint32_t) { return c4::n_moves(s); }
+    ZC_D static int count_moves_serial(const State& s, uint32_t) { return c4::n_moves(s); }
     ZC_HD static double eval(const State& s, uint32_t, int evaluator, uint64_t key) {
         if (evaluator == ZC_EVAL_C4_POSITIONAL) return c4::eval_positional(s);
         if (evaluator == ZC_EVAL_C4_ROLLOUT) return c4::eval_rollout(s, key);

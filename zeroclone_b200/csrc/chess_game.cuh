@@ -7,7 +7,7 @@
 namespace zc {
 
 struct ChessGame {
-    static constexpr int kMinBlocks = 6;   // resident 128-thread blocks per SM the fused search is compiled for
+    static constexpr int kMinBlocks = 4;   // resident 128-thread blocks per SM the fused search is compiled for
     using State = chess::Board;
     static constexpr int SS = 2;             // four bit planes = 32 bytes
     static constexpr int FIRST_SLOTS = 32;   // header + state + first 29 edges in one warp load
@@ -116,6 +116,40 @@ struct ChessGame {
             if (t - nexp == j) mine = chosen;
         }
         return mine;
+    }
+    // number of legal moves of a position, one thread, own storage (the test-only tree hash)
+    ZC_D static int count_moves_serial(const State& s, uint32_t misc) {
+        uint16_t mv[chess::MAX_PSEUDO];
+        return chess::generate(s, (int)(misc & chess::MISC_TURN), mv);
+    }
+    static constexpr bool kLazyMoves = true;    // leaves are stubs; moves are generated when a node is first expanded
+    // the move list of ONE position by the whole warp, left contiguous at the start of the warp's staging area
+    // (out of line: three call sites, and the generator is the largest piece of code in the kernel)
+    __device__ __noinline__ static int moves_warp(Ctx& gx, const State& s, uint32_t misc, int lane) {
+        return chess::generate_warp(s, (int)(misc & chess::MISC_TURN), gx.moves - lane, 1, lane);
+    }
+    // ... and packed into a node's move slots by the whole warp (8 moves per slot)
+    ZC_D static void store_moves_warp(Ctx& gx, uint4* dst, int k, int lane) {
+        const uint4* src = reinterpret_cast<const uint4*>(gx.moves - lane);
+        for (int i = lane; i < move_slots(k); i += 32) dst[i] = src[i];
+    }
+    // crude_chess_score of freshly created children (value_functions.py:49-55), one child per active lane, without
+    // their move lists: check_win = no legal move AND king attacked (chess_backend.cpp:404-412), so only a child
+    // whose side to move is in check needs to know whether it has a move -- the warp generates those lists in turn.
+    ZC_D static double eval_stubs(Ctx& gx, const State& s, uint32_t misc, bool act, int lane) {
+        const int turn = (int)(misc & 1u);
+        const bool chk = act && chess::in_check(s, turn);
+        double v = act ? (double)((turn ? -1 : 1) * chess::material(s)) : 0.0;
+        unsigned todo = __ballot_sync(FULL_MASK, chk);
+        while (todo) {
+            const int owner = __ffs((int)todo) - 1;
+            todo &= todo - 1;
+            const State os = shfl_state(s, owner);
+            const uint32_t om = __shfl_sync(FULL_MASK, misc, owner);
+            const int k = moves_warp(gx, os, om, lane);
+            if (lane == owner && k == 0) v = 1000.0;
+        }
+        return v;
     }
     ZC_HD static int count_moves(Ctx& gx, const State& s, uint32_t misc) {
         return chess::generate(s, (int)(misc & chess::MISC_TURN), gx.moves, gx.stride);

@@ -364,17 +364,48 @@ __device__ __forceinline__ int generate_warp(const Board& b, int turn, uint16_t*
             for (int d = 0; d < 8; ++d)
                 if (d < 4 ? diag : orth) seg[d] = ray_until_blocker(d, rr[d], s.occ) & targets_ok & reach;
         }
-        if (has_king && (checked || king_piece || (pinned >> sq & 1))) {   // the reference's make-move test (:345-358)
+    }
+    // The reference's make-move test (:345-358), ONE call site fed by a per-lane work list.  The common case --
+    // not in check, so only the king's own steps (and a rare pinned piece) need it -- hands the tested king's
+    // eight candidate steps to lanes 24..31, which own no piece when the side has at most 24 of them; in every
+    // other case a lane walks the targets of its own piece.
+    const int n_own = zc_popc64(s.own);
+    const bool spread_king = has_king && !checked && n_own <= 24;
+    const bool own_king_lane = mine && king_piece && sq == ksq;
+    uint64_t work = 0;                                 // targets this lane still has to test
+    int wfrom = sq;
+    bool wking = king_piece;
+    if (has_king) {
+        if (spread_king && lane >= 24) {
+#ifdef __CUDA_ARCH__
+            work = __ldg(&d_rays_t[ksq][lane - 24]) & king_targets(ksq) & targets_ok;
+#endif
+            wfrom = ksq;
+            wking = true;
+        } else if (mine && !(spread_king && own_king_lane) && (checked || king_piece || (pinned >> sq & 1))) {
 #pragma unroll
-            for (int d = 0; d < 8; ++d) {
-                uint64_t tg = seg[d];
-                while (tg) {
-                    const int t = zc_ctz64(tg);
-                    tg &= tg - 1;
-                    if (!move_keeps_king_safe(s, turn, sq, t, king_piece)) seg[d] &= ~bit(t);
-                }
-            }
+            for (int d = 0; d < 8; ++d) work |= seg[d];
         }
+    }
+    uint64_t bad = 0;
+    while (__any_sync(0xFFFFFFFFu, work != 0)) {
+        if (work) {
+            const int t = zc_ctz64(work);
+            work &= work - 1;
+            if (!move_keeps_king_safe(s, turn, wfrom, t, wking)) bad |= bit(t);
+        }
+    }
+    if (spread_king) {                                 // lanes 24..31 report their step to the king's lane
+        const uint32_t king_bad = __ballot_sync(0xFFFFFFFFu, lane >= 24 && bad != 0) >> 24;
+        if (own_king_lane) {
+#pragma unroll
+            for (int d = 0; d < 8; ++d)
+                if (king_bad >> d & 1u) seg[d] = 0;
+        }
+    }
+    if (mine && !(spread_king && lane >= 24)) {
+#pragma unroll
+        for (int d = 0; d < 8; ++d) seg[d] &= ~bad;    // a piece's segments are disjoint: a target identifies its move
     }
     int cnt = 0;
 #pragma unroll

@@ -317,13 +317,44 @@ ZC_D bool expand_spine(const SearchParams& p, typename G::Ctx& gx, uint4* __rest
 }
 
 // ---------------------------------------------------------------------------------------------
-// Chain of expansions, STEPWISE variant (chess): one lane-parallel step per chain level, because the
-// next chain node's move list must exist (a full move generation) before its children can be made.
+// Chain of expansions, STEPWISE + LAZY variant (chess): one lane-parallel step per chain level, because the
+// next chain node's move list must exist before its children can be made.  Children are created as STUBS
+// (tree.cuh) -- play the move, evaluate, write header + state -- and a node's move list is generated, by the
+// whole warp (one piece per lane), only when the search expands below it: the node the descent ends at, and
+// each node the chain steps into.  One or two warp-wide generations per batch instead of one per simulation.
 // ---------------------------------------------------------------------------------------------
+// Turn the stub at `node` into a complete node; returns its (possibly new) slot in `node` and its k.
+template <class G>
+__device__ __noinline__ bool materialize(const SearchParams& p, typename G::Ctx& gx, uint4* __restrict__ arena, TreeCtl& ctl, int lane,
+                      uint32_t& node, const typename G::State& st, uint32_t misc, int& k_out) {
+    const uint4 sh = arena[node];
+    const int k = G::moves_warp(gx, st, misc, lane);
+    k_out = k;
+    if (k == 0) {                                            // move-less node: same footprint as the stub
+        if (lane == 0) arena[node].y = 0u;
+        __syncwarp();
+        return true;
+    }
+    const uint32_t need = (uint32_t)(1 + G::SS + k + G::move_slots(k));
+    if ((uint64_t)ctl.top + need > p.arena_slots) { ctl.status = -4; return false; }
+    const uint32_t base = ctl.top;
+    for (int t = lane; t < k; t += 32) arena[base + 1 + G::SS + t] = make_uint4(0, 0, 0, 0);   // Na = 0, Wa = 0, no child
+    G::store_moves_warp(gx, arena + base + 1 + G::SS + k, k, lane);
+    if (lane == 0) {
+        arena[base] = make_hdr(sh.x, (uint32_t)k, 0, sh.z, hdr_parent_edge(sh), misc, hdr_depth(sh));
+        G::store_state(arena + base + 1, st);
+        arena[sh.z + 1 + G::SS + hdr_parent_edge(sh)].w = base;        // the parent's children[move_idx] follows the node
+    }
+    __syncwarp();
+    ctl.top += need;
+    node = base;
+    return true;
+}
+
 template <class G, bool kBuiltinEval>
-ZC_D bool expand_stepwise(const SearchParams& p, typename G::Ctx& gx, uint4* __restrict__ arena, uint2* __restrict__ path,
-                          TreeCtl& ctl, int B, int lane, uint32_t P, const uint4& hdr, const typename G::State& st,
-                          int d0, WarpPlan& wp, int& D_out, Leaf<G>& leaf) {
+ZC_D bool expand_lazy(const SearchParams& p, typename G::Ctx& gx, uint4* __restrict__ arena, uint2* __restrict__ path,
+                      TreeCtl& ctl, int B, int lane, uint32_t P, const uint4& hdr, const typename G::State& st,
+                      int d0, WarpPlan& wp, int& D_out, Leaf<G>& leaf) {
     const uint64_t tkey = p.seed ^ ((uint64_t)ctl.tree_id << 32);
     int Pk = (int)hdr_k(hdr), Pnexp = (int)hdr_nexp(hdr);
     typename G::State Pst = st;
@@ -333,6 +364,10 @@ ZC_D bool expand_stepwise(const SearchParams& p, typename G::Ctx& gx, uint4* __r
     leaf.value = 0.0;
     leaf.st = st;
     leaf.misc = Pmisc;
+    if (Pk == (int)K_UNKNOWN) {                              // the descent ended at a leaf of an earlier batch
+        if (!materialize<G>(p, gx, arena, ctl, lane, P, Pst, Pmisc, Pk)) return false;
+        Pnexp = 0;
+    }
     while (made < B) {
         if (lane == 0) wp.off[g] = made;
         if (Pk == 0) {                       // move-less node: select() returns it again and again (:59)
@@ -353,7 +388,7 @@ ZC_D bool expand_stepwise(const SearchParams& p, typename G::Ctx& gx, uint4* __r
         const int j = lane - made;
         const bool act = j >= 0 && j < m;
         const uint64_t nkey = rng_mix(tkey ^ G::state_key(Pst, Pmisc));
-        int ei = 0x7FFFFFFF, ck = 0;
+        int ei = 0x7FFFFFFF;
         typename G::State cs = Pst;
         uint32_t cmisc = 0;
         int ei_iv = 0;
@@ -361,31 +396,26 @@ ZC_D bool expand_stepwise(const SearchParams& p, typename G::Ctx& gx, uint4* __r
         if (act) {
             ei = p.policy == 3 ? ei_iv : expansion_order(p.policy, Pk, Pnexp + j, nkey);
             cs = G::child(Pst, Pmisc, arena + P, Pk, ei, cmisc);
-            ck = G::count_moves(gx, cs, cmisc);
         }
-        const int csize = act ? 1 + G::SS + ck + G::move_slots(ck) : 0;
-        int total;
-        const int off = warp_excl_scan(csize, lane, total);
+        const int total = m * (1 + G::SS);
         if ((uint64_t)ctl.top + (uint64_t)total > p.arena_slots) { ctl.status = -4; return false; }
-        const uint32_t base = ctl.top;
-        for (int t = lane; t < total; t += 32) arena[base + t] = make_uint4(0, 0, 0, 0);   // edges start at Na=0, Wa=0, no child
-        __syncwarp();
         uint32_t my_slot = 0;
         if (act) {
-            my_slot = base + (uint32_t)off;
-            arena[my_slot] = make_hdr(0, (uint32_t)ck, 0, P, (uint32_t)ei, cmisc, (uint32_t)(D + 1));
+            my_slot = ctl.top + (uint32_t)(j * (1 + G::SS));
+            arena[my_slot] = make_hdr(0, K_UNKNOWN, 0, P, (uint32_t)ei, cmisc, (uint32_t)(D + 1));
             G::store_state(arena + my_slot + 1, cs);
-            G::store_moves(gx, arena + my_slot + 1 + G::SS + ck, ck);
             arena[P + 1 + G::SS + ei].w = my_slot;                     // children[move_idx] = child (:76)
             leaf.info = (uint32_t)D | ((uint32_t)ei << LEAF_EDGE_SHIFT);
             leaf.st = cs;
             leaf.misc = cmisc;
-            if (kBuiltinEval)
-                leaf.value = G::eval_child(cs, cmisc, ck, p.evaluator, rng_mix(tkey ^ G::state_key(cs, cmisc) ^ ((uint64_t)ctl.sims_done << 40) ^ 0x51ull));
+        }
+        if (kBuiltinEval) {
+            const double v = G::eval_stubs(gx, cs, cmisc, act, lane);
+            if (act) leaf.value = v;
         }
         Pnexp += m;
         if (lane == 0) arena[P].y = (uint32_t)Pk | ((uint32_t)Pnexp << 16);   // untried.erase (:72)
-        __syncwarp();   // the new nodes (incl. their move lists) are visible to the whole warp
+        __syncwarp();
         ctl.top += (uint32_t)total;
         ctl.nodes += (uint32_t)m;
         ctl.sum_leaf_depth += (unsigned long long)m * (unsigned)(D + 1);
@@ -408,7 +438,7 @@ ZC_D bool expand_stepwise(const SearchParams& p, typename G::Ctx& gx, uint4* __r
         P = __shfl_sync(FULL_MASK, my_slot, src);
         Pst = G::shfl_state(cs, src);
         Pmisc = __shfl_sync(FULL_MASK, cmisc, src);
-        Pk = __shfl_sync(FULL_MASK, ck, src);
+        if (!materialize<G>(p, gx, arena, ctl, lane, P, Pst, Pmisc, Pk)) return false;   // its moves are needed now
         Pnexp = 0;
         ++D;
         ++g;
@@ -434,8 +464,8 @@ ZC_D bool select_expand(const SearchParams& p, typename G::Ctx& gx, uint4* __res
     typename G::State st;
     if (!descend<G>(p, arena, path, ctl, lane, P, d0, hdr, st)) return false;
     d0_out = d0;
-    if (G::kCheapSpine) return expand_spine<G, kBuiltinEval>(p, gx, arena, path, ctl, B, lane, P, hdr, st, d0, wp, D_out, leaf);
-    return expand_stepwise<G, kBuiltinEval>(p, gx, arena, path, ctl, B, lane, P, hdr, st, d0, wp, D_out, leaf);
+    if constexpr (G::kCheapSpine) return expand_spine<G, kBuiltinEval>(p, gx, arena, path, ctl, B, lane, P, hdr, st, d0, wp, D_out, leaf);
+    else return expand_lazy<G, kBuiltinEval>(p, gx, arena, path, ctl, B, lane, P, hdr, st, d0, wp, D_out, leaf);
 }
 
 // leaves that are not on the chain: their node and their edge see exactly one backprop
@@ -657,7 +687,22 @@ __global__ void k_tree_hash(const uint4* __restrict__ arena_all, uint64_t arena_
     bool entering = true;
     for (;;) {
         const uint4 hd = arena[node];
-        const uint32_t k = hdr_k(hd);
+        uint32_t k = hdr_k(hd);
+        if (k == K_UNKNOWN) {
+            // a stub stands for the leaf the reference holds with its move list and all-zero edges: hash it as that
+            const uint32_t kk = (uint32_t)G::count_moves_serial(G::load_state(arena + node + 1), hdr_misc(hd));
+            h = mix64(h, ((unsigned long long)hdr_depth(hd) << 48) ^ ((unsigned long long)kk << 32) ^
+                             ((unsigned long long)kk << 20) ^ (unsigned long long)hd.x);
+            for (uint32_t e = 0; e < kk; ++e) {
+                h = mix64(h, (unsigned long long)e << 40);
+                h = mix64(h, 0ull);
+            }
+            if (node == 0) break;
+            i = hdr_parent_edge(hd) + 1;
+            node = hd.z;
+            entering = false;
+            continue;
+        }
         if (entering) {
             h = mix64(h, ((unsigned long long)hdr_depth(hd) << 48) ^ ((unsigned long long)k << 32) ^
                              ((unsigned long long)(k - hdr_nexp(hd)) << 20) ^ (unsigned long long)hd.x);

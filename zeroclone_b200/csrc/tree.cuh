@@ -42,6 +42,13 @@ struct __align__(16) Pending {
     uint32_t info[32];   // per leaf, see LEAF_* below
 };
 
+// Games with costly move generation (chess) create a leaf as a STUB: header + state only, k = K_UNKNOWN.  The
+// reference lists a node's moves when it creates the node (mcts.cpp:74), but a leaf's list is never looked at
+// unless the search later expands below it -- about one node in thirty.  A stub is MATERIALISED (moves
+// generated, a full node written at the arena top, the parent's child link redirected) the first time the
+// search needs its moves; a stub with no moves becomes a move-less node in place.  Results are unchanged.
+constexpr uint32_t K_UNKNOWN = 0xFFFFu;
+
 constexpr uint32_t LEAF_LEVEL_MASK = 0xFFFFu;  // level of the leaf's parent (self leaf: its own level)
 constexpr int LEAF_EDGE_SHIFT = 16;            // 8 bits: edge index at the parent
 constexpr uint32_t LEAF_PATH = 1u << 30;       // the leaf is itself the next node of the chain

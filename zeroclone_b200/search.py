@@ -167,12 +167,17 @@ class TreeView:
     def __init__(self, slots: np.ndarray, state_slots: int, game: int):
         self.slots, self.ss, self.game = slots, state_slots, game
 
+    K_UNKNOWN = 0xFFFF      # a stub: header + state only, moves not generated yet (tree.cuh)
+
     def node(self, slot: int) -> dict:
         h = self.slots[slot]
         k, nexp = int(h[1] & 0xFFFF), int(h[1] >> 16)
+        stub = k == self.K_UNKNOWN
+        if stub:
+            k = 0
         e = self.slots[slot + 1 + self.ss: slot + 1 + self.ss + k]
         W = (e[:, 0].astype(np.uint64) | (e[:, 1].astype(np.uint64) << np.uint64(32))).view(np.float64) if k else np.zeros(0)
-        return {"slot": slot, "N": int(h[0]), "k": k, "nexp": nexp, "parent": int(h[2]), "parent_edge": int(h[3] & 0xFF),
+        return {"slot": slot, "N": int(h[0]), "k": k, "nexp": nexp, "stub": stub, "parent": int(h[2]), "parent_edge": int(h[3] & 0xFF),
                 "depth": int(h[3] >> 16), "Na": e[:, 2].astype(np.int64), "Wa": W, "child": e[:, 3].astype(np.int64)}
 
     def walk(self):
@@ -197,7 +202,10 @@ class TreeView:
             assert int(has.sum()) == n["nexp"], (n["slot"], "children vs n_expanded")
             assert ((n["Na"] > 0) == has).all(), (n["slot"], "visited edge without child or child without visit")
             assert (np.abs(n["Wa"]) <= n["Na"] * max_abs_value + 1e-9).all(), (n["slot"], "value sum out of range")
-            if n["slot"] == 0:
+            if n["stub"]:
+                # evaluated once when it was created; the first descent that reaches it makes it a complete node
+                assert n["N"] == 1 and n["slot"] != 0, (n["slot"], "stub with N != 1")
+            elif n["slot"] == 0:
                 assert n["N"] == int(n["Na"].sum()), "root N"
             elif n["k"] > 0:
                 assert n["N"] == 1 + int(n["Na"].sum()), (n["slot"], "N != 1 + sum Na")
