@@ -73,7 +73,8 @@ struct ChessGame {
     // Which move the t-th expansion of a node picks is a function of the node (its key seeds the draws), so the
     // warp replays picks 0 .. nexp+m-1 (lane L owns moves L, L+32, ...) and lane j receives the move of
     // expansion nexp + j.  Called by the whole warp.
-    ZC_D static int immediate_value_order(const uint4* node, const State& st, int k, int nexp, int m, int j, float freedom,
+    // (out of line: only Policy.immediate_value runs it)
+    __device__ __noinline__ static int immediate_value_order(const uint4* node, const State& st, int k, int nexp, int m, int j, float freedom,
                                           uint64_t key, int lane) {
         constexpr int Q = (ZC_MAX_MOVES + 31) / 32;
         int val[Q];

@@ -112,6 +112,13 @@ ZC_HD uint64_t first_blocker(int d, uint64_t blockers) {
     if (dir_ascending(d)) return blockers & (0 - blockers);
     return blockers ? bit(63 - zc_clz64(blockers)) : 0ull;
 }
+// is the first occupied square met along a ray a member of `set` (a subset of the blockers)?  For a descending
+// direction that is "the highest bit of blockers belongs to set": set's part outweighs the rest as a number.
+ZC_HD bool first_blocker_in(int d, uint64_t blockers, uint64_t set) {
+    const uint64_t a = blockers & set;
+    if (dir_ascending(d)) return ((blockers & (0 - blockers)) & a) != 0;
+    return a > (blockers ^ a);
+}
 // squares of `ray` (the squares beyond some origin in direction d) up to and including the first blocker
 ZC_HD uint64_t ray_until_blocker(int d, uint64_t ray, uint64_t occ) {
     const uint64_t f = first_blocker(d, ray & occ);
@@ -132,8 +139,10 @@ ZC_HD bool square_attacked(int side, int ksq, uint64_t occ, uint64_t e_pawn, uin
     if (e_diag | e_orth) {
         uint64_t r[8];
         rays_of<0, 8>(ksq, r);
+        bool ray_hit = false;
 #pragma unroll
-        for (int d = 0; d < 8; ++d) hit |= first_blocker(d, r[d] & occ) & (d < 4 ? e_diag : e_orth);
+        for (int d = 0; d < 8; ++d) ray_hit |= first_blocker_in(d, r[d] & occ, d < 4 ? e_diag : e_orth);
+        if (ray_hit) return true;
     }
     return hit != 0;
 }

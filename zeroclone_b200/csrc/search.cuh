@@ -152,18 +152,14 @@ ZC_D bool descend(const SearchParams& p, const uint4* __restrict__ arena, uint2*
         double best = -CUDART_INF;
         int best_e = 0x7FFFFFFF;
         uint32_t best_child = 0;
-        {
-            const int e = lane - (1 + G::SS);
-            if (e >= 0 && e < k && lane < G::FIRST_SLOTS) {
-                best = uct(edge_W(v), (int)v.z, logN, p.c);
-                best_e = e;
-                best_child = v.w;
-            }
-        }
-        for (int e = G::FIRST_SLOTS - (1 + G::SS) + lane; e < k; e += 32) {   // wide nodes (chess)
-            const uint4 ev = np[1 + G::SS + e];
+        // lane L looks at edges L - (1+SS), +32, ...: the first round comes out of the warp load above, wide
+        // (chess) nodes take further rounds; ascending e per lane, so strict > keeps the lowest index
+        for (int slot = lane; slot < 1 + G::SS + k; slot += 32) {
+            const int e = slot - (1 + G::SS);
+            if (e < 0) continue;
+            const uint4 ev = slot < G::FIRST_SLOTS ? v : np[slot];
             const double u = uct(edge_W(ev), (int)ev.z, logN, p.c);
-            if (u > best) { best = u; best_e = e; best_child = ev.w; }       // ascending e: strict > keeps the lowest
+            if (u > best) { best = u; best_e = e; best_child = ev.w; }
         }
 #pragma unroll
         for (int d = 16; d >= 1; d >>= 1) {
