@@ -252,7 +252,7 @@ def run_ours(args):
     tree_bytes_step = sims_done * (node_bytes + 4 + 20) + batches * (depth + 1) * (node_bytes + 2 * 20)
     # measured DRAM traffic per simulation of the tree kernels: dram__bytes_read+write of one `ncu --set full`
     # capture of k_search_fused divided by the simulations of that launch (profiles/r1d_k_search_fused_chess_ncu.txt, r1b_k_search_fused_c4_ncu.txt)
-    ncu_bytes_per_sim = 589.0 if chess else 148.0
+    ncu_bytes_per_sim = 80.0 if chess else 148.0
     roofline_tree = {"bound": "hbm", "achieved": tree_bytes_step * args.steps / (tree_ms * 1e-3) / 1e9 if tree_ms else None,
                      "peak": hbm_peak, "unit": "GB/s",
                      "traffic": None if use_net else ncu_bytes_per_sim * sims_done,

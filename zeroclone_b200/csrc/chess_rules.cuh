@@ -313,6 +313,9 @@ ZC_HD int generate(const Board& b, int turn, uint16_t* out, int stride = 1) {
 }
 
 #ifdef __CUDACC__
+// out of line: reached only for a contrived position with more than 32 pieces of one colour
+__device__ __noinline__ int generate_cold(const Board& b, int turn, uint16_t* out, int stride) { return generate(b, turn, out, stride); }
+
 // The same list as generate(), produced by a whole warp for ONE position: lane r owns the side to move's
 // r-th piece in square order (the order the reference scans, chess_backend.cpp:203), builds that piece's
 // targets as up to eight ordered segments (one per direction for sliders and the king -- queen_dirs /
@@ -324,7 +327,7 @@ __device__ __forceinline__ int generate_warp(const Board& b, int turn, uint16_t*
     const Sets s = derive(b, turn);
     if (zc_popc64(s.own) > 32) {                       // more pieces than lanes (only a contrived FEN): one lane does it
         int n = 0;
-        if (lane == 0) n = generate(b, turn, out, stride);
+        if (lane == 0) n = generate_cold(b, turn, out, stride);
         return __shfl_sync(0xFFFFFFFFu, n, 0);
     }
     const uint64_t empty = ~s.occ;
