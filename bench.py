@@ -290,7 +290,7 @@ def run_ours(args):
                        "algorithmic_bytes_per_sim": tree_bytes_step / sims_done},
     }
     if args.selfplay_games < 0:     # enough games in flight to occupy the GPU, few enough to finish in seconds
-        args.selfplay_games = {"c4_value_net": 2048, "c4_heuristic": 16384, "chess_crude": 4096, "chess_value_net": 512}[args.workload]
+        args.selfplay_games = {"c4_value_net": 2048, "c4_heuristic": 16384, "chess_crude": 16384, "chess_value_net": 512}[args.workload]
     if args.selfplay_games > 0:
         # secondary half of the metric: self-play games/hour with the full move loop on the device
         # (search, apply move, win/draw detection, refill); not part of the timed steps above

@@ -118,22 +118,26 @@ class DeviceSelfPlay:
                                                            res.ctypes.data_as(C.c_void_p), mv.ctypes.data_as(C.c_void_p), stream))
                 plies += n
                 new_host = roots.cpu().numpy().view(self.init_rec.dtype).reshape(n) if record else None
+                # bookkeeping per ply, vectorised: which games ended, which slots get the next game (refill
+                # semantics of simulate_games, scripts/train.py:151-170)
+                act = np.asarray(active, dtype=np.int64)
+                if record:
+                    for j, slot in enumerate(active):
+                        traj[slot_game[slot]].append(new_host[j].copy())
+                done = np.nonzero(res != _ffi.RESULT_ONGOING)[0]
+                keep = np.ones(n, dtype=bool)
                 refill = []
-                still = []
-                for j, slot in enumerate(active):
-                    g = slot_game[slot]
-                    if record:
-                        traj[g].append(new_host[j].copy())
-                    if res[j] == _ffi.RESULT_ONGOING:
-                        still.append(slot)
-                        continue
-                    results[g] = int(res[j])
+                for j in done:                       # a handful per ply
+                    slot = int(act[j])
+                    results[slot_game[slot]] = int(res[j])
                     finished += 1
                     if started < total_games:
                         slot_game[slot] = started
                         started += 1
-                        refill.append(j)
-                        still.append(slot)
+                        refill.append(int(j))
+                    else:
+                        keep[j] = False
+                still = act[keep].tolist()
                 states_all.index_copy_(0, idx, roots)
                 if refill:
                     ridx = idx[torch.tensor(refill, dtype=torch.long, device=dev)]
