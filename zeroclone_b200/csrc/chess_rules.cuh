@@ -345,9 +345,9 @@ __device__ __forceinline__ int generate_warp(const Board& b, int turn, uint16_t*
     bool king_piece = false;
     const bool mine = lane < zc_popc64(s.own);
     if (mine) {
-        uint64_t m = s.own;
-        for (int i = 0; i < lane; ++i) m &= m - 1;
-        sq = zc_ctz64(m);
+        const uint32_t lo = (uint32_t)s.own, hi = (uint32_t)(s.own >> 32);   // square of the own piece of rank `lane`
+        const int n_lo = __popc(lo);
+        sq = lane < n_lo ? (int)__fns(lo, 0, lane + 1) : 32 + (int)__fns(hi, 0, lane - n_lo + 1);
         const int type = piece_at(b, sq) & 7, r = sq >> 3, c = sq & 7;
         if (type == PAWN) {                            // single push, double push, capture dc=-1, capture dc=+1
             const int dir = turn == 0 ? -1 : 1, home = turn == 0 ? 6 : 1;
