@@ -15,14 +15,20 @@
 //   - a horizontal shift wraps into the neighbouring board at x = 0 / W-1.  The three tap columns
 //     (dx = -1, 0, +1) therefore accumulate into three TMEM accumulators and the epilogue adds the
 //     dx = -1 (dx = +1) accumulator only to rows with x != 0 (x != W-1);
-//   - tcgen05.mma (cta_group::1, kind::f16, bf16 x bf16 -> fp32, M = N = 128, K = 16) issued by one
-//     thread; per layer and tile 9 taps x 8 k-steps;
-//   - weights: one 32 KB image per (layer, tap) already in the shared-memory layout, fetched with
-//     cp.async.bulk into a ring of stages (mbarrier complete_tx);
-//   - epilogue (8 warps): tcgen05.ld the three accumulators, bias (+ residual, kept in registers as
-//     packed bf16) + ReLU, write the next layer's input in place; two tiles per CTA alternate so the
-//     epilogue of one overlaps the MMAs of the other; accumulators rotate through the 4 x 128 TMEM columns;
-//   - after the last block: per-row dot with the head weights, per-board sum in a fixed order, tanh.
+//   - tcgen05.mma kind::f16 (bf16 x bf16 -> fp32), K = 16, issued by one elected thread from warp-uniform
+//     control flow; per layer and tile 9 taps x 8 k-steps.  CTAs run as PAIRS (cta_group::2, M = 256 over two
+//     SMs): each CTA keeps its own 128-row tile and HALF of every tap's weights (64 of the 128 output
+//     channels), rank 0 issues for both -- the single-CTA form is bound by shared-memory bandwidth;
+//   - weights: one 16 KB image per (layer, tap, CTA rank) already in the shared-memory layout of the B operand,
+//     fetched with cp.async.bulk into an 8-stage ring (mbarrier complete_tx); rank 1 relays "my half has
+//     landed" to rank 0 with a remote mbarrier arrive, tcgen05.commit multicast frees a stage in both CTAs;
+//   - epilogue (8 warps): phase 1 reads the two side accumulators, applies the edge masks and hands their
+//     TMEM columns back at once; phase 2 reads the centre accumulator, adds bias (shared memory) and the
+//     residual (kept in registers as packed bf16 for the whole block), ReLU, and overwrites the tile in place.
+//     Two tiles per CTA alternate so the epilogue of one runs under the MMAs of the other; accumulators
+//     rotate through the 4 x 128 TMEM columns;
+//   - after the last block: per-row dot with the head weights, per-board sum in a fixed order, tanh;
+//   - every mbarrier wait is bounded: a protocol bug ends the kernel with an error instead of hanging the GPU.
 #pragma once
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
