@@ -121,7 +121,8 @@ int zc_c4_get_move_order(uint8_t *table /* [128][8] */);
 /* ---- search handle: replaces get_move() for a whole batch of trees ----------------------- */
 
 /* arena_slots_per_tree: 16-byte slots per tree, 0 = default (C4: exact worst case;
- * chess: (max_sims+1) * 72).  Memory = max_trees * arena_slots_per_tree * 16 B. */
+ * chess: (max_sims+1) * 24 -- leaves are 3-slot stubs, about 5 slots per node in practice; an arena that
+ * overflows makes zc_search_results return ZC_ECAPACITY).  Memory = max_trees * arena_slots_per_tree * 16 B. */
 int zc_search_create(int game, int device, int max_trees, int max_sims, int64_t arena_slots_per_tree,
                      zc_search **out);
 int zc_search_destroy(zc_search *h);
