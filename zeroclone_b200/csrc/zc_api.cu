@@ -311,7 +311,8 @@ extern "C" int zc_search_create(int game, int device, int max_trees, int max_sim
     // chess: stubs are 3 slots and about one node in thirty becomes a complete node (~37 slots): 4.9 slots per
     // node measured on configs[4]; 24 leaves a factor 5, and an arena that does overflow is reported, not truncated
     const int per_node = game == ZC_GAME_C4 ? 1 + C4Game::SS + 7 : 24;
-    h->arena_slots = arena_slots_per_tree > 0 ? (uint64_t)arena_slots_per_tree : (uint64_t)(max_sims + 1) * per_node;
+    h->arena_slots = arena_slots_per_tree > 0 ? (uint64_t)arena_slots_per_tree
+                                              : (uint64_t)(max_sims + 1) * per_node + (game == ZC_GAME_C4 ? 0 : 320);   // + a maximal chess root
     h->arena_slots = (h->arena_slots + 1) & ~1ull;   // keep every tree's arena 32-byte aligned
     h->path_cap = (uint32_t)max_sims + 40u;
     auto alloc = [&](void** p, size_t bytes) -> cudaError_t {
