@@ -57,6 +57,21 @@ def test_c4_full_size_value_net_split_phase():
     check_sampled(ts, n, sims, 1.0, sample=12)
 
 
+def test_chess_full_size_value_net_split_phase():
+    """BASELINE configs[3]: 2048 trees x 800 sims, stub leaves + the fused tower on 17x8x8 planes"""
+    n, sims = 2048, 800
+    torch.manual_seed(0)
+    from zeroclone_b200.models.chess_value.network import ValueNetwork
+    ev = NetEvaluator(ValueNetwork().eval(), "cuda")
+    ts = TreeSearch(_ffi.GAME_CHESS, n, sims)
+    ts.set_roots(chess_roots_set_b(n))
+    ts.run_network(ev, sims, 1.4, 32, _ffi.POLICY_FIRST)
+    check_sampled(ts, n, sims, 1.0, sample=12)
+    c = ts.counters()
+    assert c["simulations"] == n * sims
+    assert c["arena_slots_used"] < 8 * c["nodes"], "leaves should be 3-slot stubs"
+
+
 @pytest.mark.parametrize("policy", [_ffi.POLICY_FIRST, _ffi.POLICY_RANDOM])
 def test_chess_full_size_2048_trees_1600_sims(policy):
     n, sims = 2048, 1600
