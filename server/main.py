@@ -1,56 +1,45 @@
-"""REST wrapper over `Engine` with the reference's wire format (server/main.py:14-112 of the reference):
-GET /legal_moves/{idx}, POST /play_move, POST /play_mcts, POST /add_game, GET /state/{idx}.
-`/play_mcts` runs the batched CUDA search; everything else is host bookkeeping."""
-import argparse
-import collections
-import os
-from contextlib import asynccontextmanager
-from typing import Any, Optional
+"""HTTP front of `Engine` speaking the reference's wire format (its server/main.py:14-112): five routes --
+legal moves, play a move, let the search play, open a game, read a state -- and the state serialiser the PHP
+board expects.  Only `/play_mcts` touches the GPU (one batched CUDA search); the rest is host bookkeeping.
 
-from fastapi import FastAPI, HTTPException
+    python -m server.main -c configs/crude_chess.yaml --port 8000
+    CONFIG_PATH=configs/connect4.yaml uvicorn server.main:app
+"""
+import argparse
+import os
+from collections import deque
+from contextlib import asynccontextmanager
+from typing import Any, Callable, Optional
+
+from fastapi import APIRouter, FastAPI, HTTPException, Request
 from pydantic import BaseModel
 
 from engine.engine import Engine
 
+_SCALARS = (bool, int, float, str)
+
 
 def serialize_state(state: object) -> dict:
-    """board as a list; every public int/float/str/bool attribute by name; deques as lists
-    (server/main.py:14-36).  Works for the chess `State` (nine fields, bindings_chess.cpp:13-41) and the
-    Connect Four namedtuple alike."""
-    out: dict = {}
+    """Wire form of a backend state: `board` as a list when it can be listed, then every public attribute that is
+    a plain scalar, deques flattened to lists.  (pybind11 hands the chess histories over as lists, which the
+    reference's serialiser skips -- so they are not part of the format, here as there.)"""
+    wire: dict = {}
+    board = getattr(state, "board", None)
     if hasattr(state, "board"):
-        board = state.board
         try:
-            out["board"] = list(board)
+            wire["board"] = list(board)
         except TypeError:
-            out["board"] = board
-    for name in dir(state):
-        if name.startswith("_") or name == "board":
-            continue
+            wire["board"] = board
+    for attr in (a for a in dir(state) if a != "board" and not a.startswith("_")):
         try:
-            value = getattr(state, name)
+            value = getattr(state, attr)
         except Exception:
             continue
-        if isinstance(value, (bool, int, float, str)):
-            out[name] = value
-        elif isinstance(value, collections.deque):
-            out[name] = list(value)
-    return out
-
-
-config_path: Optional[str] = None
-
-
-@asynccontextmanager
-async def lifespan(app: FastAPI):
-    cfg = config_path or os.getenv("CONFIG_PATH")
-    if not cfg:
-        raise RuntimeError("Config file path must be set: `python -m server.main -c <yaml>` or CONFIG_PATH")
-    app.state.engine = Engine(cfg)
-    yield
-
-
-app = FastAPI(lifespan=lifespan)
+        if isinstance(value, deque):
+            wire[attr] = list(value)
+        elif isinstance(value, _SCALARS):
+            wire[attr] = value
+    return wire
 
 
 class MoveRequest(BaseModel):
@@ -64,66 +53,94 @@ class MCTSRequest(BaseModel):
     c: float = 1.4
 
 
-def _guard(fn):
+config_path: Optional[str] = None      # set by main(); CONFIG_PATH is the alternative
+routes = APIRouter()
+
+
+def _engine(request: Request) -> Engine:
+    return request.app.state.engine
+
+
+def _answer(work: Callable[[], dict]) -> dict:
+    """every failure is a 400 carrying the exception text, as in the reference"""
     try:
-        return fn()
+        return work()
     except HTTPException:
         raise
-    except Exception as exc:      # the reference answers every failure with 400 + the message
+    except Exception as exc:
         raise HTTPException(status_code=400, detail=str(exc))
 
 
-@app.get("/legal_moves/{idx}")
-def legal_moves(idx: int):
-    return _guard(lambda: {"idx": idx, "moves": [list(m[0]) if isinstance(m[0], (tuple, list)) else [m[0]]
-                                                 for m in app.state.engine.legal_moves(idx)]})
+def _with_state(eng: Engine, idx: int, **head) -> dict:
+    return {"idx": idx, **head, **serialize_state(eng.get_state(idx))}
 
 
-@app.post("/play_move")
-def play_move(req: MoveRequest):
-    def run():
-        eng = app.state.engine
-        wanted = tuple(req.move) if isinstance(req.move, (list, tuple)) else req.move
-        legal = next((mv for mv in eng.legal_moves(req.idx)
-                      if mv[0] == wanted or (isinstance(wanted, tuple) and len(wanted) == 1 and mv[0] == wanted[0])), None)
-        if legal is None:
-            raise ValueError("Illegal move")
-        result = eng.play_move(legal, req.idx)
-        return {"idx": req.idx, "result": result, **serialize_state(eng.get_state(req.idx))}
-    return _guard(run)
+def _coords(move) -> list:
+    first = move[0]
+    return list(first) if isinstance(first, (tuple, list)) else [first]
 
 
-@app.post("/play_mcts")
-def play_mcts(req: MCTSRequest):
-    def run():
-        eng = app.state.engine
-        result = eng.play_mcts(req.idx, req.simulations, req.c)
-        return {"idx": req.idx, "result": result, **serialize_state(eng.get_state(req.idx))}
-    return _guard(run)
+@routes.get("/legal_moves/{idx}")
+def legal_moves(idx: int, request: Request):
+    return _answer(lambda: {"idx": idx, "moves": [_coords(m) for m in _engine(request).legal_moves(idx)]})
 
 
-@app.post("/add_game")
-def add_game():
-    return _guard(lambda: {"idx": app.state.engine.add_game()})
+@routes.post("/play_move")
+def play_move(req: MoveRequest, request: Request):
+    def work():
+        eng = _engine(request)
+        wanted = req.move
+        key = tuple(wanted) if isinstance(wanted, (list, tuple)) else (wanted,)
+        for candidate in eng.legal_moves(req.idx):
+            if tuple(_coords(candidate)) == key:
+                return _with_state(eng, req.idx, result=eng.play_move(candidate, req.idx))
+        raise ValueError("Illegal move")
+    return _answer(work)
 
 
-@app.get("/state/{idx}")
-def get_state(idx: int):
-    return _guard(lambda: {"idx": idx, **serialize_state(app.state.engine.get_state(idx))})
+@routes.post("/play_mcts")
+def play_mcts(req: MCTSRequest, request: Request):
+    def work():
+        eng = _engine(request)
+        return _with_state(eng, req.idx, result=eng.play_mcts(req.idx, req.simulations, req.c))
+    return _answer(work)
+
+
+@routes.post("/add_game")
+def add_game(request: Request):
+    return _answer(lambda: {"idx": _engine(request).add_game()})
+
+
+@routes.get("/state/{idx}")
+def get_state(idx: int, request: Request):
+    return _answer(lambda: _with_state(_engine(request), idx))
+
+
+@asynccontextmanager
+async def _lifespan(application: FastAPI):
+    chosen = config_path or os.getenv("CONFIG_PATH")
+    if not chosen:
+        raise RuntimeError("Config file path must be set: `python -m server.main -c <yaml>` or CONFIG_PATH")
+    application.state.engine = Engine(chosen)
+    yield
+
+
+app = FastAPI(lifespan=_lifespan)
+app.include_router(routes)
 
 
 def main() -> None:
     import uvicorn
 
-    ap = argparse.ArgumentParser(description="REST server for the game engine")
-    ap.add_argument("-c", "--config", required=True, help="game configuration YAML")
-    ap.add_argument("--host", default="0.0.0.0")
-    ap.add_argument("--port", type=int, default=8000)
-    args = ap.parse_args()
+    cli = argparse.ArgumentParser(description="REST server for the game engine")
+    cli.add_argument("-c", "--config", required=True, help="game configuration YAML")
+    cli.add_argument("--host", default="0.0.0.0")
+    cli.add_argument("--port", type=int, default=8000)
+    opts = cli.parse_args()
     global config_path
-    config_path = args.config
-    os.environ["CONFIG_PATH"] = args.config
-    uvicorn.run(app, host=args.host, port=args.port)
+    config_path = opts.config
+    os.environ["CONFIG_PATH"] = opts.config
+    uvicorn.run(app, host=opts.host, port=opts.port)
 
 
 if __name__ == "__main__":

@@ -1,89 +1,100 @@
 """The value tower shared by every game: stem conv3x3 -> N residual blocks -> GAP -> Linear -> tanh.
 
-Architecture and parameter names follow the reference's models/chess_value/network.py:9-45 so
-that state_dicts (and whole-module pickles saved by scripts/train.py:143) interchange:
-`stem.0/1`, `res.<i>.seq.0/1/3/4`, `head.2`.  Only the input plane count differs per game.
+Sub-module names (`stem.0/1`, `res.<i>.seq.0/1/3/4`, `head.2`) and their creation order follow the reference's
+models/chess_value/network.py:9-45, so state_dicts and the whole-module pickles written by scripts/train.py:143
+interchange, and the same seed builds the same weights (tests/test_network_golden.py relies on it).  Only the
+input plane count differs per game.  This module is the fp32 definition: checkpoints, training, the reference
+forward of the parity tests.  Inference during search runs in csrc/tower.cuh from its BatchNorm-folded weights.
 """
 from __future__ import annotations
+
+from typing import Callable, Iterable, Optional
 
 import numpy as np
 import torch
 from torch import nn
 from torch.utils.data import Dataset
 
+KERNEL = dict(kernel_size=3, padding=1, bias=False)
+
+
+def _conv_bn(cin: int, cout: int) -> list:
+    return [nn.Conv2d(cin, cout, **KERNEL), nn.BatchNorm2d(cout)]
+
 
 class ResidualBlock(nn.Module):
+    """x -> relu(x + bn(conv(relu(bn(conv(x))))))"""
+
     def __init__(self, c: int):
         super().__init__()
-        self.seq = nn.Sequential(
-            nn.Conv2d(c, c, 3, padding=1, bias=False), nn.BatchNorm2d(c), nn.ReLU(inplace=True),
-            nn.Conv2d(c, c, 3, padding=1, bias=False), nn.BatchNorm2d(c))
+        first, second = _conv_bn(c, c), _conv_bn(c, c)
+        self.seq = nn.Sequential(*first, nn.ReLU(inplace=True), *second)
         self.relu = nn.ReLU(inplace=True)
 
     def forward(self, x):
-        return self.relu(x + self.seq(x))
+        return self.relu(self.seq(x) + x)
 
 
 class ValueTower(nn.Module):
-    in_planes = 17
+    in_planes = 17      # chess; subclasses override (Connect Four: 2)
 
-    def __init__(self, channels: int = 128, blocks: int = 8, in_planes: int | None = None):
+    def __init__(self, channels: int = 128, blocks: int = 8, in_planes: Optional[int] = None):
         super().__init__()
-        if in_planes is not None:
-            self.in_planes = in_planes
-        self.stem = nn.Sequential(nn.Conv2d(self.in_planes, channels, 3, padding=1, bias=False),
-                                  nn.BatchNorm2d(channels), nn.ReLU(inplace=True))
+        self.in_planes = self.in_planes if in_planes is None else in_planes
+        self.stem = nn.Sequential(*_conv_bn(self.in_planes, channels), nn.ReLU(inplace=True))
         self.res = nn.Sequential(*[ResidualBlock(channels) for _ in range(blocks)])
         self.head = nn.Sequential(nn.AdaptiveAvgPool2d(1), nn.Flatten(), nn.Linear(channels, 1), nn.Tanh())
 
-    def forward(self, x):
-        return self.head(self.res(self.stem(x)))
+    def forward(self, planes):
+        return self.head(self.res(self.stem(planes)))
 
 
 class ValueNetDataset(Dataset):
-    """(states float32[N,C,H,W], values float32[N]) -> tensors; reference network.py:47-56."""
+    """positions float32[N,C,H,W] with their targets float32[N] (the arrays Engine.get_dataset returns)"""
 
     def __init__(self, states: np.ndarray, values: np.ndarray):
-        self.states = torch.from_numpy(np.asarray(states)).float()
-        self.values = torch.from_numpy(np.asarray(values)).float()
+        self.states = torch.as_tensor(np.asarray(states), dtype=torch.float32)
+        self.values = torch.as_tensor(np.asarray(values), dtype=torch.float32)
+        assert len(self.states) == len(self.values)
 
-    def __len__(self):
-        return self.states.shape[0]
+    def __len__(self) -> int:
+        return int(self.values.shape[0])
 
     def __getitem__(self, i):
         return self.states[i], self.values[i]
 
 
-def safe_globals(*extra):
-    """Classes a whole-module checkpoint needs under torch.load(weights_only=True); network.py:58-71."""
-    torch.serialization.add_safe_globals([
-        ResidualBlock, ValueTower, nn.Conv2d, nn.BatchNorm2d, nn.ReLU, nn.AdaptiveAvgPool2d, nn.Linear, nn.Tanh,
-        nn.Sequential, nn.Flatten, *extra])
+def safe_globals(*extra) -> None:
+    """register what torch.load(weights_only=True) must be allowed to unpickle for a whole-module checkpoint"""
+    layers = (nn.Sequential, nn.Conv2d, nn.BatchNorm2d, nn.ReLU, nn.AdaptiveAvgPool2d, nn.Flatten, nn.Linear, nn.Tanh)
+    torch.serialization.add_safe_globals([ValueTower, ResidualBlock, *layers, *extra])
+
+
+def _one_epoch(model, batches: Iterable, optimiser, device, grad_sync: Optional[Callable]) -> float:
+    """sum over the epoch of (batch loss x batch size)"""
+    weighted = 0.0
+    for planes, target in batches:
+        planes, target = planes.to(device), target.to(device).unsqueeze(1)
+        optimiser.zero_grad()
+        loss = nn.functional.mse_loss(model(planes), target)
+        loss.backward()
+        if grad_sync is not None:      # multi-GPU: average gradients over ranks (one NCCL all-reduce)
+            grad_sync(model)
+        optimiser.step()
+        weighted += loss.item() * planes.shape[0]
+    return weighted
 
 
 def train(model, dataloader, epochs: int = 10, lr: float = 1e-3, device=None, grad_sync=None):
-    """Adam + MSE loop with the reference's signature and return value (network.py:75-101):
-    the mean over epochs of the per-sample average loss.  `grad_sync`, if given, is called between
-    backward() and step() -- the insertion point of the NCCL gradient all-reduce."""
+    """Adam on the mean squared error, `epochs` passes over `dataloader`; returns the mean over epochs of the
+    per-sample loss (what the reference's train() returns, network.py:75-101).  `grad_sync(model)`, if given,
+    runs between backward() and step() -- the place where the reference would need its gradient all-reduce."""
     device = device or ("cuda" if torch.cuda.is_available() else "cpu")
     model.to(device)
-    opt = torch.optim.Adam(model.parameters(), lr=lr)
-    mse = nn.MSELoss()
-    total = 0.0
-    for epoch in range(1, epochs + 1):
+    optimiser = torch.optim.Adam(model.parameters(), lr=lr)
+    history = []
+    for epoch in range(epochs):
         model.train()
-        seen = 0.0
-        for states, targets in dataloader:
-            states = states.to(device)
-            targets = targets.to(device).unsqueeze(1)
-            opt.zero_grad()
-            loss = mse(model(states), targets)
-            loss.backward()
-            if grad_sync is not None:
-                grad_sync(model)
-            opt.step()
-            seen += loss.item() * states.size(0)
-        epoch_loss = seen / len(dataloader.dataset)
-        total += epoch_loss
-        print(f"Epoch {epoch}/{epochs} — Loss: {epoch_loss:.4f}")
-    return total / epochs
+        history.append(_one_epoch(model, dataloader, optimiser, device, grad_sync) / len(dataloader.dataset))
+        print(f"Epoch {epoch + 1}/{epochs} — Loss: {history[-1]:.4f}")
+    return sum(history) / epochs
