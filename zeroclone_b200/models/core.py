@@ -7,11 +7,11 @@ import importlib
 from pathlib import Path
 from typing import List, Tuple
 
-MODELS_DIR = Path(__file__).resolve().parent
+_ROOT = Path(__file__).resolve().parent
 
 
 def _home(model_type: str) -> Path:
-    return MODELS_DIR / model_type
+    return _ROOT / model_type
 
 
 def get_value_network(model_type: str) -> Tuple[object, Path]:
