@@ -168,3 +168,23 @@ def test_c4_boards_with_gaps_follow_the_reference(L):
     _ffi.check(L.zc_c4_play_move(C.byref(s), 3, C.byref(n)))
     ref = zo.c4_play(zo.c4_from_rows(rows, 1), 3)
     assert c4_unpack_rows(n.x, n.o) == zo.c4_rows(ref) and n.turn == ref.turn
+
+
+def test_treeview_decodes_stub_leaves():
+    """host-side decoding of the arena layout (tree.cuh): a chess leaf is a stub (k = 0xFFFF, header + state)"""
+    from zeroclone_b200.search import TreeView
+    ss = 2
+    slots = np.zeros((16, 4), dtype=np.uint32)
+    # root at slot 0: N = 1, k = 2 moves, 1 expanded; edges at slots 3, 4; moves at slot 5
+    slots[0] = (1, 2 | (1 << 16), 0, 0)
+    w = np.array([-3.0], dtype=np.float64).view(np.uint32)
+    slots[3] = (w[0], w[1], 1, 6)            # edge 0: Wa = -3, Na = 1, child at slot 6
+    # stub child at slot 6: N = 1, k unknown, parent 0, parent edge 0, depth 1
+    slots[6] = (1, 0xFFFF, 0, 0 | (1 << 16))
+    tv = TreeView(slots, ss, _ffi.GAME_CHESS)
+    child = tv.node(6)
+    assert child["stub"] and child["k"] == 0 and child["N"] == 1 and child["depth"] == 1
+    assert tv.check_invariants(max_abs_value=1000.0) == 2
+    slots[6][0] = 2                           # a stub is evaluated exactly once
+    with pytest.raises(AssertionError):
+        TreeView(slots, ss, _ffi.GAME_CHESS).check_invariants(max_abs_value=1000.0)
