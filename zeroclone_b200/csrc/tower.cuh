@@ -183,6 +183,33 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo, uint3
 constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
 constexpr uint32_t IDESC2 = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) << 17) | ((256u >> 4) << 24);   // M = 256 over the pair
 
+// two fp32 lanes per instruction (FADD2 / FMUL2 / FFMA2): the epilogue's arithmetic in half the issue slots
+__device__ __forceinline__ uint64_t f2_pack(uint32_t lo, uint32_t hi) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi));
+    return r;
+}
+__device__ __forceinline__ void f2_unpack(uint64_t v, float& lo, float& hi) {
+    uint32_t a, b;
+    asm("mov.b64 {%0, %1}, %2;" : "=r"(a), "=r"(b) : "l"(v));
+    lo = __uint_as_float(a);
+    hi = __uint_as_float(b);
+}
+__device__ __forceinline__ uint64_t f2_add(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ uint64_t f2_mul(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ uint64_t f2_fma(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
     __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
     return *reinterpret_cast<uint32_t*>(&h);
@@ -416,6 +443,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) k_value_tower(const Params p) {
         }
 
         const float fm = x != 0 ? 1.f : 0.f, fp = x != G::W - 1 ? 1.f : 0.f;   // horizontal taps that stay on the board
+        const uint64_t fm2 = f2_pack(__float_as_uint(fm), __float_as_uint(fm)), fp2 = f2_pack(__float_as_uint(fp), __float_as_uint(fp));
         uint32_t gbase = 0;   // first accumulator group of the current step
         for (int m = 0; m < steps_per_slot; ++m) {
             const int layer = m % NL, it = m / NL;
@@ -423,6 +451,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) k_value_tower(const Params p) {
             const float fres = (layer != 0 && (layer & 1) == 0) ? 1.f : 0.f;   // second conv of a block adds its input (network.py:20-21)
             const bool keep = (layer & 1) == 0;                                // output is the next block's input
             const float4* sb = reinterpret_cast<const float4*>(smem + SMEM_BIAS) + (layer * CH + half * 64) / 4;
+            const uint64_t fres2 = f2_pack(__float_as_uint(fres), __float_as_uint(fres));
 #pragma unroll
             for (int slot = 0; slot < NT; ++slot, gbase += 3) {
                 mbar_wait(bar_accfull + 8 * slot, (uint32_t)m & 1u, p.fault, 5);
@@ -430,7 +459,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) k_value_tower(const Params p) {
                 uint8_t* arow = smem + SMEM_ABUF + slot * A_BUF_BYTES + (HALO + r) * 16;
                 // phase 1: the two side accumulators (dx = -1, +1), masked at the board edges, into registers;
                 // their TMEM columns go back to the MMA issuer before the rest of the epilogue runs
-                float side[64];
+                uint64_t side[32];                 // pairs of channels
 #pragma unroll
                 for (int cc = 0; cc < 4; ++cc) {
                     const uint32_t col = half * 64 + cc * 16;
@@ -439,7 +468,8 @@ __global__ void __launch_bounds__(N_THREADS, 1) k_value_tower(const Params p) {
                     tc_ld16(tlane + ((gbase + 2) & 3u) * 128u + col, ap);
                     tc_wait_ld();
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) side[cc * 16 + i] = fmaf(fp, __uint_as_float(ap[i]), fm * __uint_as_float(am[i]));
+                    for (int i = 0; i < 16; i += 2)
+                        side[cc * 8 + (i >> 1)] = f2_fma(fp2, f2_pack(ap[i], ap[i + 1]), f2_mul(fm2, f2_pack(am[i], am[i + 1])));
                 }
                 tc_fence_before();
                 signal(pfree_dst + 8 * slot);
@@ -458,12 +488,11 @@ __global__ void __launch_bounds__(N_THREADS, 1) k_value_tower(const Params p) {
                         for (int e = 0; e < 4; e += 2) {
                             const int i = q * 4 + e;
                             const uint32_t xr = xreg[slot][cc * 8 + (i >> 1)];
-                            float v0 = __uint_as_float(a0[i]) + side[cc * 16 + i];
-                            float v1 = __uint_as_float(a0[i + 1]) + side[cc * 16 + i + 1];
-                            v0 += bv[e];
-                            v1 += bv[e + 1];
-                            v0 = fmaf(fres, bf16_lo(xr), v0);
-                            v1 = fmaf(fres, bf16_hi(xr), v1);
+                            uint64_t v = f2_add(f2_pack(a0[i], a0[i + 1]), side[cc * 8 + (i >> 1)]);
+                            v = f2_add(v, f2_pack(__float_as_uint(bv[e]), __float_as_uint(bv[e + 1])));
+                            v = f2_fma(fres2, f2_pack(xr << 16, xr & 0xFFFF0000u), v);
+                            float v0, v1;
+                            f2_unpack(v, v0, v1);
                             const uint32_t pk = pack_bf16(fmaxf(v0, 0.f), fmaxf(v1, 0.f));
                             o[i >> 1] = pk;
                             xreg[slot][cc * 8 + (i >> 1)] = keep ? pk : xr;
