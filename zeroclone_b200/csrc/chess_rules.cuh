@@ -110,7 +110,12 @@ ZC_HD constexpr bool dir_ascending(int d) { return d == 2 || d == 3 || d == 5 ||
 // an ascending direction, highest for a descending one
 ZC_HD uint64_t first_blocker(int d, uint64_t blockers) {
     if (dir_ascending(d)) return blockers & (0 - blockers);
+#ifdef __CUDA_ARCH__
+    const uint64_t r = __brevll(blockers);                   // highest bit = lowest bit of the bit-reversed word
+    return __brevll(r & (0 - r));
+#else
     return blockers ? bit(63 - zc_clz64(blockers)) : 0ull;
+#endif
 }
 // is the first occupied square met along a ray a member of `set` (a subset of the blockers)?  For a descending
 // direction that is "the highest bit of blockers belongs to set": set's part outweighs the rest as a number.
@@ -432,11 +437,12 @@ __device__ __forceinline__ int generate_warp(const Board& b, int turn, uint16_t*
     int pos = x - cnt;
 #pragma unroll
     for (int d = 0; d < 8; ++d) {
-        uint64_t tg = seg[d];
+        const bool up = (asc >> d & 1u) != 0;          // outward from the piece: ascending squares, or descending
+        uint64_t tg = up ? seg[d] : __brevll(seg[d]);  // (walked as ascending bits of the reversed word)
         while (tg) {
-            const int t = (asc >> d & 1u) ? zc_ctz64(tg) : 63 - zc_clz64(tg);
-            tg &= ~bit(t);
-            out[(size_t)(pos++) * stride] = pack_move(sq, t);
+            const int i = zc_ctz64(tg);
+            tg &= tg - 1;
+            out[(size_t)(pos++) * stride] = pack_move(sq, up ? i : 63 - i);
         }
     }
     __syncwarp();
