@@ -138,3 +138,18 @@ def test_tower_soak_random_batches_bit_identical():
         assert torch.equal(ev(x[off:off + n].contiguous()), ref[off:off + n]), (launches, n, off)
         launches += 1
     assert launches > 500
+
+
+@pytest.mark.parametrize("blocks", [1, 3])
+def test_tower_with_fewer_blocks(blocks):
+    """the kernel takes the number of residual blocks from the model (<= 8, the reference's depth)"""
+    from zeroclone_b200.models.connect4_value.network import ValueNetwork
+    torch.manual_seed(4)
+    model = ValueNetwork(blocks=blocks).eval()
+    x = random_planes(700, (2, 6, 7), 3)
+    with torch.no_grad():
+        ref = model(x).view(-1)
+    got = NetEvaluator(model, "cuda")(x.to("cuda", torch.bfloat16)).cpu()
+    assert (got - ref).abs().max().item() < TOL
+    with pytest.raises(Exception):
+        NetEvaluator(ValueNetwork(blocks=9).eval(), "cuda")
