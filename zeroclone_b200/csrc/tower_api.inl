@@ -4,7 +4,6 @@
 
 struct zc_tower {
     int game = 0, device = 0, n_layers = 0, cin = 0;
-    uint8_t* wimg = nullptr;
     uint8_t* wimg2 = nullptr;
     float* bias = nullptr;
     float* head_w = nullptr;
@@ -39,23 +38,20 @@ extern "C" int zc_tower_create(int game, int device, int n_blocks, const float* 
     using namespace zc::tower;
     const int cin = game == ZC_GAME_C4 ? GeomC4::CIN : GeomChess::CIN;
     const int nl = 1 + 2 * n_blocks;
-    // weight images in the shared-memory layout of the B operand: [layer][tap][k-chunk][n][8] bf16,
-    // taps ordered by column offset first (dx = -1, 0, +1), then row offset (dy = -1, 0, +1).
+    // weight images in the shared-memory layout of the B operand, split by halves of N:
+    // [layer][tap][n / 64][k-chunk][n % 64][8] bf16 -- the part each CTA of a cta_group::2 pair keeps in its own
+    // shared memory; taps ordered by column offset first (dx = -1, 0, +1), then row offset (dy = -1, 0, +1).
     // conv_w is PyTorch's [Cout][Cin][kH][kW] per layer, stem first (cross-correlation: dy = kh-1, dx = kw-1).
-    // img2 is the same data split by halves of N: [layer][tap][n / 64][k-chunk][n % 64][8], the part of the
-    // B operand each CTA of a cta_group::2 pair keeps in its own shared memory.
-    std::vector<uint16_t> img((size_t)nl * 9 * KCHUNKS * CH * 8, 0), img2(img.size(), 0);
+    std::vector<uint16_t> img2((size_t)nl * 9 * KCHUNKS * CH * 8, 0);
     size_t woff = 0;
     for (int l = 0; l < nl; ++l) {
         const int ci = l == 0 ? cin : CH;
         for (int g = 0; g < 3; ++g)
             for (int dyi = 0; dyi < 3; ++dyi) {
-                uint16_t* dst = img.data() + ((size_t)l * 9 + g * 3 + dyi) * KCHUNKS * CH * 8;
                 uint16_t* dst2 = img2.data() + ((size_t)l * 9 + g * 3 + dyi) * KCHUNKS * CH * 8;
                 for (int n = 0; n < CH; ++n)
                     for (int k = 0; k < ci; ++k) {
                         const uint16_t v = f32_to_bf16_rne(conv_w[woff + (((size_t)n * ci + k) * 3 + dyi) * 3 + g]);
-                        dst[((size_t)(k / 8) * CH + n) * 8 + (k % 8)] = v;
                         dst2[(((size_t)(n / 64) * KCHUNKS + k / 8) * 64 + n % 64) * 8 + (k % 8)] = v;
                     }
             }
@@ -69,7 +65,7 @@ extern "C" int zc_tower_create(int game, int device, int n_blocks, const float* 
     t->head_b = head_b;
     t->n_sms = prop.multiProcessorCount;
     auto cleanup = [&](int rc) {
-        cudaFree(t->wimg); cudaFree(t->wimg2); cudaFree(t->bias); cudaFree(t->head_w); cudaFree(t->fault);
+        cudaFree(t->wimg2); cudaFree(t->bias); cudaFree(t->head_w); cudaFree(t->fault);
         delete t;
         return rc;
     };
@@ -78,12 +74,10 @@ extern "C" int zc_tower_create(int game, int device, int n_blocks, const float* 
         cudaError_t _e = (expr);                                                                           \
         if (_e != cudaSuccess) return cleanup(fail(ZC_ECUDA, std::string(#expr) + ": " + cudaGetErrorString(_e))); \
     } while (0)
-    TOWER_TRY(cudaMalloc(&t->wimg, img.size() * 2));
     TOWER_TRY(cudaMalloc(&t->wimg2, img2.size() * 2));
     TOWER_TRY(cudaMalloc(&t->bias, sizeof(float) * nl * CH));
     TOWER_TRY(cudaMalloc(&t->head_w, sizeof(float) * CH));
     TOWER_TRY(cudaMalloc(&t->fault, sizeof(unsigned int)));
-    TOWER_TRY(cudaMemcpy(t->wimg, img.data(), img.size() * 2, cudaMemcpyHostToDevice));
     TOWER_TRY(cudaMemcpy(t->wimg2, img2.data(), img2.size() * 2, cudaMemcpyHostToDevice));
     TOWER_TRY(cudaMemcpy(t->bias, conv_b, sizeof(float) * nl * CH, cudaMemcpyHostToDevice));
     TOWER_TRY(cudaMemcpy(t->head_w, head_w, sizeof(float) * CH, cudaMemcpyHostToDevice));
@@ -98,7 +92,6 @@ extern "C" int zc_tower_create(int game, int device, int n_blocks, const float* 
 extern "C" void zc_tower_destroy(zc_tower* t) {
     if (!t) return;
     cudaSetDevice(t->device);
-    cudaFree(t->wimg);
     cudaFree(t->wimg2);
     cudaFree(t->bias);
     cudaFree(t->head_w);
@@ -114,7 +107,7 @@ extern "C" int zc_tower_forward(zc_tower* t, const void* dev_planes_bf16, int n_
     CUDA_TRY(cudaSetDevice(t->device));
     Params p;
     p.planes = reinterpret_cast<const __nv_bfloat16*>(dev_planes_bf16);
-    p.wimg = t->wimg;
+    p.wimg = nullptr;      // the single-CTA layout is not instantiated
     p.wimg2 = t->wimg2;
     p.bias = t->bias;
     p.head_w = t->head_w;
