@@ -163,6 +163,14 @@ int zc_search_backprop(zc_search *h, const float *dev_values, void *stream);
 int zc_search_results(zc_search *h, zc_root_result *results, int32_t *visits, double *value_sums,
                       zc_chess_move *moves, int stride, void *stream);
 
+/* The same readout (chosen move and counters per tree, no per-child arrays) without stalling the host:
+ * _begin enqueues the readout kernel on `stream` and the device->pinned-host copy on the handle's own copy
+ * stream, so the next zc_search_set_roots_dev / zc_search_run can be enqueued immediately (device results are
+ * double-buffered); _end waits for the most recent _begin and copies results[n] out (ZC_ECAPACITY as above).
+ * This is how a self-play loop pipelines searches of a few milliseconds (scripts/train.py:151-170). */
+int zc_search_results_begin(zc_search *h, void *stream);
+int zc_search_results_end(zc_search *h, zc_root_result *results);
+
 /* Order-dependent 64-bit hash over every node and edge of each tree (same function as
  * oracle/zc_oracle.c:hash_tree): equality means the whole tree matches the reference's bit for bit. */
 int zc_search_tree_hash(zc_search *h, uint64_t *host_hashes, void *stream);
@@ -232,6 +240,10 @@ int zc_c4_rules_batch(int device, const zc_c4_state *states, int n, uint8_t *col
  * (most-visited child, mcts.cpp:150-155), apply it to dev_states[i] (zc_c4_state / zc_chess_state
  * records in device memory, the array that was given to zc_search_set_roots_dev), and evaluate the new
  * position: check_win -> new.turn*2-1, check_draw -> 0, else ZC_RESULT_ONGOING.
+ * Never silent: if a tree outgrew its arena during the search (ZC_ECAPACITY), an active tree has no visited
+ * root move (ZC_ESTATE: no simulation ran or the root is terminal), or a chess side's history is full
+ * (ZC_ECAPACITY: grow hist_cap), that tree's state is left unchanged with ZC_RESULT_ONGOING and the call
+ * fails; zc_last_error() names the lowest offending tree.
  * Chess: dev_hist holds each side's moves [n][2][hist_cap] in playing order (zc_chess_move), dev_hist_len
  * [n][2]; both are updated (chess_backend.cpp:374) and used for the repetition rule (:148-180,434-438);
  * the fifty-ply counter lives in the state record.  C4: pass NULL for both.
@@ -263,6 +275,14 @@ int zc_tower_create(int game, int device, int n_blocks, const float *conv_w, con
                     float head_b, zc_tower **out);
 void zc_tower_destroy(zc_tower *t);
 int zc_tower_forward(zc_tower *t, const void *dev_planes_bf16, int n_leaves, float *dev_values, void *stream);
+/* New weights into an existing tower (same arguments as zc_tower_create): what the training loop does after
+ * every cycle (scripts/train.py:143-146 saves latest.pth and the next self-play evaluates with it).  The weight
+ * image is re-packed on the host and uploaded on `stream`, ordered after the forwards already enqueued there. */
+int zc_tower_update_weights(zc_tower *t, const float *conv_w, const float *conv_b, const float *head_w, float head_b,
+                            void *stream);
+/* After a failed launch or synchronisation: the kernel's own fault word (0 = none; else 0x80000000 | wait tag,
+ * written when a bounded barrier wait timed out -- a protocol bug, never expected).  Clears it. */
+unsigned int zc_tower_fault(zc_tower *t);
 int64_t zc_tower_launches(const zc_tower *t);
 
 #ifdef __cplusplus

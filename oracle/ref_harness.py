@@ -1,28 +1,50 @@
-"""TEST/BENCH INFRASTRUCTURE: drive the UNMODIFIED reference search (oracle/_ref/mcts*.so,
-compiled from the reference's engine/mcts/src/*.cpp by oracle/Makefile) on the box's host cores.
+"""TEST/BENCH INFRASTRUCTURE: drive the UNMODIFIED reference on the box's host cores.
 
-The reference's Connect Four backend and its Value/Policy classes are Python files that cannot
-travel to the GPU box, so the callbacks the C++ search needs are restated here, with the same
-object shapes the reference uses (namedtuple state with list-of-lists board, set-valued
-get_legal_moves, value.batch(states, backend=), policy(list)).  Used only by bench.py
-(--impl reference and the cpu_baseline leg) and by tests.
+`make -C oracle ref` lays the reference's own files of the hot path out under oracle/_ref/pyref/
+as its `engine` and `models` packages: the two pybind11 modules compiled from its C++ sources
+(engine/mcts/src/*.cpp, engine/games/chess/src/*.cpp) and, verbatim, engine/value_functions.py,
+engine/policy_functions.py, engine/games/connect4/c4_backend.py, engine/mcts/__init__.py and
+models/.  This file imports THOSE (never this repo's packages, never libzc_b200.so) and runs
+`engine.mcts.get_move(state, Value, policy, backend, sims, c, batch)` -- the call
+engine/engine.py:119-129 makes -- one tree at a time on every host core.
+
+Nothing is restated here except three things the reference does not ship:
+  * a `first`-untried policy callback (the parity configuration's deterministic policy; the stock
+    Policy class only has random / immediate_value, policy_functions.py:10-17),
+  * `c4_positional`, the deterministic Connect Four parity evaluator, added as a
+    method of a subclass of the stock Value so it runs through the stock Value.batch/__call__,
+  * a Connect Four value network: the reference has models/chess_value only, so configs[1] uses the
+    stock chess_value.ValueNetwork class with its stem convolution re-made for 2 input planes.
+The network evaluator is the stock Value._nn_setup / _batch_worker / batch path
+(value_functions.py:61-99) on the CPU (CUDA is hidden from the workers: DEVICE="cpu", fp32).
+
+Timing: worker processes are persistent; imports, model construction and root decoding happen
+before the clock; each step every worker times its own get_move loop with perf_counter and the
+step's value is the sum of the workers' own sims/second (they run concurrently, one per core).
+
+Used only by bench.py (`--impl reference`, the cpu_baseline leg) and tests.
 """
 from __future__ import annotations
 
 import os
 import sys
-from collections import namedtuple
+import time
 
 import numpy as np
 
 _REF_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
+PYREF = os.path.join(_REF_DIR, "pyref")
+C_UCT, BATCH = 1.4, 32
 
 
 def ref_available() -> bool:
-    return os.path.isdir(_REF_DIR) and any(f.startswith("mcts") and f.endswith(".so") for f in os.listdir(_REF_DIR))
+    d = os.path.join(PYREF, "engine", "mcts")
+    return (os.path.isdir(d) and any(f.startswith("mcts") and f.endswith(".so") for f in os.listdir(d))
+            and os.path.exists(os.path.join(PYREF, "engine", "value_functions.py")))
 
 
 def ref_modules():
+    """the two compiled reference modules on their own (tests)"""
     if _REF_DIR not in sys.path:
         sys.path.insert(0, _REF_DIR)
     import chess_backend
@@ -30,89 +52,243 @@ def ref_modules():
     return mcts, chess_backend
 
 
-# ---- Connect Four backend with the reference's object shapes (c4_backend.py:4-61) ------------
-C4State = namedtuple("State", ["board", "turn"])
-_TOK = "XO"
+class _Stock:
+    pass
 
 
-class C4Backend:
-    @staticmethod
-    def create_init_state():
-        return C4State([[" "] * 7 for _ in range(6)], 0)
-
-    @staticmethod
-    def from_bits(x: int, o: int, turn: int):
-        b = [[" "] * 7 for _ in range(6)]
-        for r in range(6):
-            for c in range(7):
-                bit = 1 << (c * 7 + (5 - r))
-                if x & bit:
-                    b[r][c] = "X"
-                elif o & bit:
-                    b[r][c] = "O"
-        return C4State(b, turn)
-
-    @staticmethod
-    def play_move(state, move):
-        col = move[0]
-        board = [list(r) for r in state.board]
-        for r in range(5, -1, -1):
-            if board[r][col] == " ":
-                board[r][col] = _TOK[state.turn]
-                break
-        return C4State(board, 1 - state.turn)
-
-    @staticmethod
-    def check_win(state):
-        t = _TOK[1 - state.turn]
-        b = state.board
-        for r in range(6):
-            for c in range(7):
-                if b[r][c] != t:
-                    continue
-                for dr, dc in ((0, 1), (1, 0), (1, 1), (-1, 1)):
-                    rr, cc = r + 3 * dr, c + 3 * dc
-                    if 0 <= rr < 6 and 0 <= cc < 7 and all(b[r + i * dr][c + i * dc] == t for i in (1, 2, 3)):
-                        return True
-        return False
-
-    @staticmethod
-    def check_draw(state):
-        return all(cell != " " for row in state.board for cell in row)
-
-    @staticmethod
-    def get_legal_moves(state):
-        return {(c, 0) for c in range(7) if state.board[0][c] == " "}
-
-    @staticmethod
-    def state_to_tensor(state):
-        cur, opp = _TOK[state.turn], _TOK[1 - state.turn]
-        a = np.array(state.board)
-        return np.stack([(a == cur), (a == opp)]).astype(np.float32)
+_stock = None
 
 
-class TorchValue:
-    """value.batch(states, backend=) as engine/value_functions.py:24-32,78-99 compute it (stack the
-    state tensors, one fp32 forward, list of floats), minus the worker thread and queues."""
-
-    def __init__(self, model):
-        import torch
-        self.torch = torch
-        self.model = model.eval()
-
-    def batch(self, states, backend=None):
-        x = self.torch.from_numpy(np.stack([backend.state_to_tensor(s) for s in states]))
-        with self.torch.no_grad():
-            return self.model(x).view(-1).tolist()
-
-
-class FnValue:
-    def __init__(self, fn):
-        self.fn = fn
-
-    def batch(self, states, backend=None):
-        return [self.fn(s, backend) for s in states]
+def stock(need_torch: bool = False) -> _Stock:
+    """Import the reference's own `engine` / `models` packages from oracle/_ref/pyref.  This repo ships
+    import aliases of the same names at its root (drop-in for users); they must not win here."""
+    global _stock
+    if _stock is None:
+        if not ref_available():
+            raise ImportError("oracle/_ref/pyref is missing: run `make -C oracle ref` where /root/reference exists")
+        for name in list(sys.modules):
+            if name in ("engine", "models") or name.startswith(("engine.", "models.")):
+                f = getattr(sys.modules[name], "__file__", None) or ""
+                if not f.startswith(PYREF):
+                    del sys.modules[name]
+        sys.path.insert(0, PYREF)
+        import importlib
+        s = _Stock()
+        s.mcts = importlib.import_module("engine.mcts")
+        s.c4 = importlib.import_module("engine.games.connect4.c4_backend")
+        s.chess = importlib.import_module("engine.games.chess.chess_backend")
+        s.Policy = importlib.import_module("engine.policy_functions").Policy
+        for m in (s.mcts, s.c4, s.chess):
+            assert m.__file__.startswith(PYREF), (m.__name__, m.__file__)
+        assert s.mcts.mcts is not None, "reference engine.mcts could not load its compiled module"
+        _stock = s
+    if need_torch and not hasattr(_stock, "Value"):
+        import importlib
+        vf = importlib.import_module("engine.value_functions")      # imports torch; DEVICE is decided here
+        assert vf.__file__.startswith(PYREF)
+        _stock.vf = vf
+        _stock.Value = vf.Value
+        _stock.network = importlib.import_module("models.chess_value.network")
+    return _stock
 
 
 def first_policy(moves):
     return moves[0]
+
+
+# ---- root sets (SURVEY.md §8d set B) from the reference's own backends ---------------------------
+def c4_roots_set_b(n: int, first_tree_id: int = 0) -> list:
+    """[(x_bits, o_bits, turn)]: the same positions as zeroclone_b200.workloads.c4_roots_set_b, produced by
+    playing the reference's c4_backend (legal moves in list(set) order, c4_backend.py:49-50)."""
+    b = stock().c4
+    out = []
+    for i in range(n):
+        tid = first_tree_id + i
+        rng = np.random.Generator(np.random.PCG64(1234 + tid))
+        while True:
+            s = b.create_init_state()
+            for _ in range(tid % 13):
+                moves = list(b.get_legal_moves(s))
+                s = b.play_move(s, moves[int(rng.integers(len(moves)))])
+            if not b.check_win(s) and not b.check_draw(s):
+                break
+        x = o = 0
+        for r in range(6):
+            for c in range(7):
+                bit = 1 << (c * 7 + (5 - r))
+                if s.board[r][c] == "X":
+                    x |= bit
+                elif s.board[r][c] == "O":
+                    o |= bit
+        out.append((x, o, int(s.turn)))
+    return out
+
+
+def c4_state_from_bits(x: int, o: int, turn: int):
+    b = stock().c4
+    board = [[" "] * 7 for _ in range(6)]
+    for r in range(6):
+        for c in range(7):
+            bit = 1 << (c * 7 + (5 - r))
+            if x & bit:
+                board[r][c] = "X"
+            elif o & bit:
+                board[r][c] = "O"
+    return b.State(board, turn)
+
+
+def chess_roots_set_b(n: int, first_tree_id: int = 0) -> list:
+    """[72-byte packed zc_chess_state]: same positions as zeroclone_b200.workloads.chess_roots_set_b, produced by the
+    reference's chess_backend (get_legal_moves / play_move / check_win / check_draw incl. its own histories)."""
+    b = stock().chess
+    out = []
+    for i in range(n):
+        tid = first_tree_id + i
+        rng = np.random.Generator(np.random.PCG64(1234 + tid))
+        while True:
+            s = b.create_init_state()
+            for _ in range(tid % 13):
+                mv = b.get_legal_moves(s)
+                if not mv:
+                    break
+                s = b.play_move(s, mv[int(rng.integers(len(mv)))])
+            if not b.check_win(s) and not b.check_draw(s):
+                break
+        out.append(bytes(s.board) + bytes([s.turn, s.fifty_move_rule_counter, s.w_ck, s.w_cq, s.b_ck, s.b_cq, 0, 0]))
+    return out
+
+
+def chess_state_from_bytes(raw: bytes):
+    b = stock().chess
+    return b.State(list(raw[:64]), raw[64], raw[65], bool(raw[66]), bool(raw[67]), bool(raw[68]), bool(raw[69]), [], [])
+
+
+# ---- evaluators --------------------------------------------------------------------------------
+def make_value(game: str, evaluator: str):
+    """A stock `Value` for the workload's evaluator."""
+    if evaluator == "value_net":
+        s = stock(need_torch=True)
+        import torch
+        torch.set_num_threads(1)
+        torch.manual_seed(0)
+        model = s.network.ValueNetwork()
+        if game == "connect4":       # the reference ships no Connect Four network: same tower, 2 input planes
+            model.stem[0] = torch.nn.Conv2d(2, 128, 3, padding=1, bias=False)
+        v = s.Value.__new__(s.Value)         # init_network_latest (value_functions.py:104-112) minus the checkpoint lookup
+        v.name, v.init_args = "network_latest", {"batch_size": BATCH}
+        v._nn_setup(model, BATCH)
+        assert v.device == "cpu", "the reference arm is the reference's CPU path"
+        return v
+    s = stock(need_torch=True)             # value_functions.py imports torch at module level
+    if evaluator == "chess_crude":
+        return s.Value("crude_chess_score")
+    if evaluator == "c4_positional":
+        w = (1, 2, 3, 4, 3, 2, 1)
+
+        class ParityValue(s.Value):
+            def c4_positional(self, state, args):
+                if args["backend"].check_win(state):
+                    return -1
+                cur = "XO"[state.turn]
+                return sum((w[c] if cell == cur else -w[c]) for row in state.board for c, cell in enumerate(row) if cell != " ") / 64
+        return ParityValue("c4_positional")
+    if evaluator == "random_rollout":
+        return s.Value("random_rollout")
+    raise ValueError(evaluator)
+
+
+# ---- persistent worker pool --------------------------------------------------------------------
+def _worker_main(conn, game, evaluator, rows, sims):
+    try:
+        os.environ["CUDA_VISIBLE_DEVICES"] = ""        # the reference's Value then picks DEVICE="cpu", fp32
+        os.environ.setdefault("OMP_NUM_THREADS", "1")
+        s = stock(need_torch=True)
+        value = make_value(game, evaluator)
+        if game == "chess":
+            backend = s.chess
+            states = [chess_state_from_bytes(r) for r in rows]
+        else:
+            backend = s.c4
+            states = [c4_state_from_bits(*r) for r in rows]
+        get_move = s.mcts.get_move
+        conn.send(("ready", os.getpid()))
+        nxt = 0
+        while True:
+            msg = conn.recv()
+            if msg[0] == "stop":
+                break
+            budget = msg[1]
+            done = 0
+            t0 = time.perf_counter()
+            while True:
+                get_move(states[nxt % len(states)], value, first_policy, backend, sims, C_UCT, BATCH)
+                nxt += 1
+                done += sims
+                dt = time.perf_counter() - t0
+                if dt >= budget:
+                    break
+            conn.send(("done", done, dt))
+    except Exception as e:      # noqa: BLE001 -- reported to the parent, which raises
+        import traceback
+        conn.send(("error", f"{e!r}\n{traceback.format_exc()}"))
+
+
+class RefPool:
+    """`cores` persistent processes, each owning a slice of the root set.  step(seconds) -> (sims/s, detail)."""
+
+    def __init__(self, game: str, evaluator: str, rows: list, sims: int, cores: int | None = None):
+        import multiprocessing as mp
+        if cores is None:
+            cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+        self.cores, self.sims = cores, sims
+        # spawn, not fork: the parent may hold a CUDA context (cpu_baseline leg of the GPU arm) and this repo's
+        # `engine` aliases; the workers start from a clean interpreter with CUDA hidden
+        ctx = mp.get_context("spawn")
+        per = max(1, len(rows) // cores)
+        self.procs, self.conns = [], []
+        saved = {k: os.environ.get(k) for k in ("CUDA_VISIBLE_DEVICES", "OMP_NUM_THREADS", "MKL_NUM_THREADS")}
+        os.environ.update({"CUDA_VISIBLE_DEVICES": "", "OMP_NUM_THREADS": "1", "MKL_NUM_THREADS": "1"})
+        try:
+            for i in range(cores):
+                a, b = ctx.Pipe()
+                mine = rows[i * per:(i + 1) * per] or rows[:1]
+                p = ctx.Process(target=_worker_main, args=(b, game, evaluator, mine, sims), daemon=True)
+                p.start()
+                self.procs.append(p)
+                self.conns.append(a)
+        finally:
+            for k, v in saved.items():
+                if v is None:
+                    os.environ.pop(k, None)
+                else:
+                    os.environ[k] = v
+        for c in self.conns:
+            self._expect(c, "ready")
+
+    @staticmethod
+    def _expect(conn, what):
+        msg = conn.recv()
+        if msg[0] == "error":
+            raise RuntimeError("reference worker failed: " + msg[1])
+        assert msg[0] == what, msg
+        return msg
+
+    def step(self, seconds: float):
+        for c in self.conns:
+            c.send(("go", seconds))
+        res = [self._expect(c, "done") for c in self.conns]
+        rate = sum(d / dt for _, d, dt in res)
+        total = sum(d for _, d, _ in res)
+        longest = max(dt for _, _, dt in res)
+        return rate, {"sims": total, "trees": total // self.sims, "longest_worker_s": longest}
+
+    def close(self):
+        for c in self.conns:
+            try:
+                c.send(("stop",))
+            except Exception:
+                pass
+        for p in self.procs:
+            p.join(timeout=10)
+            if p.is_alive():
+                p.kill()

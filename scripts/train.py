@@ -5,7 +5,7 @@ checkpoint,  with the reference's hyper-parameter schedule and CSV stats rows.
 
 Multi-GPU (torchrun, one process per GPU): every rank self-plays its shard of the games with its own
 engine (no collective), trains on its own positions, and the gradients are averaged with ONE NCCL
-all-reduce per step (zeroclone_b200.parallel.GradSync -- the insertion point the reference leaves
+all-reduce per step (zeroclone_b200.training / parallel.GradSync -- the insertion point the reference leaves
 between loss.backward() and optimizer.step(), models/chess_value/network.py:93-94).  Rank 0 writes
 `latest.pth` (whole-module pickle, train.py:143) and rotates the previous one into checkpoints/.
 
@@ -31,6 +31,7 @@ from zeroclone_b200 import parallel  # noqa: E402
 from zeroclone_b200.engine import Engine  # noqa: E402
 from zeroclone_b200.models import core  # noqa: E402
 from zeroclone_b200.selfplay import DeviceSelfPlay  # noqa: E402
+from zeroclone_b200.training import train_epochs  # noqa: E402
 
 _REPLAY_STATES: list = []
 _REPLAY_VALUES: list = []
@@ -71,34 +72,17 @@ def schedule_hyperparams(cycle, *, games_cap=2000, sims_cap=800, init_lr=3e-4, l
 
 
 def train_and_save_latest(model_type, model, states, values, *, epochs, lr, batch_size, device, rank, world):
-    """Adam + MSE on (states, values) (network.py:75-101) with data-parallel gradient averaging; every rank
-    runs the same number of steps (the longest shard's), shorter shards wrap around."""
+    """Adam + MSE on (states, values) (network.py:75-101), data-parallel (zeroclone_b200.training.train_epochs: one
+    flat NCCL all-reduce per step, no host sync inside the step, BatchNorm statistics averaged over ranks at the end);
+    rank 0 then rotates the previous checkpoint and saves the new `latest.pth` (train.py:136-146)."""
     module, latest_path = core.get_value_network(model_type)
-    model.to(device).train()
-    sync = parallel.GradSync(model)
-    sync.broadcast_parameters(0)
-    opt = torch.optim.Adam(model.parameters(), lr=lr)
-    xs = torch.from_numpy(states).float().to(device)
-    ys = torch.from_numpy(values).float().to(device).unsqueeze(1)
-    n = len(xs)
-    steps = int(parallel.reduce_max([-(-n // batch_size)])[0])
-    total = 0.0
-    for epoch in range(1, epochs + 1):
-        perm = torch.randperm(n, device=device) if n else None
-        running = 0.0
-        for s in range(steps):
-            idx = perm[(torch.arange(batch_size, device=device) + s * batch_size) % n]
-            opt.zero_grad()
-            loss = torch.nn.functional.mse_loss(model(xs[idx]), ys[idx])
-            loss.backward()
-            sync(model, n_samples=len(idx))
-            opt.step()
-            running += loss.item() * len(idx)
-        avg = running / max(1, steps * batch_size)
-        total += avg
-        if rank == 0:
-            print(f"Epoch {epoch}/{epochs} — Loss: {avg:.4f}")
+    stats = train_epochs(model, states, values, epochs=epochs, lr=lr, batch_size=batch_size, device=device, rank=rank,
+                         timed=world > 1 and device.type == "cuda")
     if rank == 0:
+        if "allreduce_ms" in stats:
+            gbs = stats["allreduce_bytes"] / (stats["allreduce_ms_median"] * 1e-3) / 1e9
+            print(f"train step {stats['step_ms']:.2f} ms; gradient all-reduce {stats['allreduce_bytes'] / 1e6:.2f} MB in "
+                  f"{stats['allreduce_ms_median'] * 1e3:.0f} us (median of {stats['allreduce_calls']}) = {gbs:.0f} GB/s algorithmic")
         ckpt = Path(latest_path).parent / "checkpoints"
         ckpt.mkdir(parents=True, exist_ok=True)
         if Path(latest_path).exists():                      # rotate (train.py:136-141)
@@ -106,7 +90,7 @@ def train_and_save_latest(model_type, model, states, values, *, epochs, lr, batc
         torch.save(model.to("cpu"), latest_path)
         model.to(device)
         print("Saved new *latest* model to", latest_path)
-    return total / max(1, epochs)
+    return stats["loss"]
 
 
 def full_training_run(config_name, *, cycles=30, batch_size=256, epochs=4, games_cap=2000, sims_cap=800, init_lr=3e-4,
@@ -146,7 +130,7 @@ def full_training_run(config_name, *, cycles=30, batch_size=256, epochs=4, games
             loss_acc += train_and_save_latest(model_type, value.model, states, values, epochs=epochs, lr=hp["lr"],
                                               batch_size=batch_size, device=device, rank=rank, world=world)
         value.model.eval()
-        value._net = None          # self-play of the next cycle evaluates with the freshly trained weights
+        value.refresh()            # the resident tower takes the freshly trained weights (zc_tower_update_weights)
     if rank == 0:
         emit_stats(stage="train_done", cycle=cycles, loss=loss_acc / max(1, cycles), epochs=epochs)
     if torch.distributed.is_available() and torch.distributed.is_initialized():

@@ -12,7 +12,7 @@ from contextlib import asynccontextmanager
 from typing import Any, Callable, Optional
 
 from fastapi import APIRouter, FastAPI, HTTPException, Request
-from pydantic import BaseModel
+from pydantic import BaseModel, Field
 
 from engine.engine import Engine
 
@@ -49,7 +49,8 @@ class MoveRequest(BaseModel):
 
 class MCTSRequest(BaseModel):
     idx: int = 0
-    simulations: int = 1000
+    # bounded: the search handle's node arena is sized from this number (sims+1 nodes per tree)
+    simulations: int = Field(1000, ge=1, le=200_000)
     c: float = 1.4
 
 

@@ -50,7 +50,17 @@ def _worker(rank, world, port, q):
     torch.nn.functional.mse_loss(model(x[lo:lo + n_r]), y[lo:lo + n_r]).backward()
     sync(model, n_samples=n_r)
     flat_w = torch.cat([p.grad.view(-1) for p in model.parameters()])
-    q.put((rank, all_shards, tmax, tsum, flat.numpy(), flat_w.numpy()))
+    assert sync.calls == 2                     # one collective per step
+    # the training step of scripts/train.py with uneven shards, one of them EMPTY: same number of collectives on
+    # both ranks, identical parameters and BatchNorm statistics afterwards
+    from zeroclone_b200.training import train_epochs
+    n_mine = 0 if r == 0 else 40
+    xs_t = torch.randn(n_mine, 2, 6, 7, generator=g).numpy()
+    ys_t = torch.randn(n_mine, generator=g).numpy()
+    st = train_epochs(model, xs_t, ys_t, epochs=2, lr=1e-3, batch_size=16, device=torch.device("cpu"), rank=r, verbose=False)
+    assert st["steps"] == 2 * 3 and st["positions"] == n_mine
+    state = torch.cat([t.detach().float().view(-1) for t in list(model.parameters()) + [b for b in model.buffers() if b.dtype.is_floating_point]])
+    q.put((rank, all_shards, tmax, tsum, flat.numpy(), flat_w.numpy(), state.numpy()))
     dist.destroy_process_group()
 
 
@@ -65,7 +75,8 @@ def test_world_size_2_gloo():
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    (_, shards0, tmax0, tsum0, g0, gw0), (_, shards1, tmax1, tsum1, g1, gw1) = got
+    (_, shards0, tmax0, tsum0, g0, gw0, st0), (_, shards1, tmax1, tsum1, g1, gw1, st1) = got
+    assert np.array_equal(st0, st1) and np.isfinite(st0).all()      # ranks end the training step with the same network
     assert shards0 == shards1 == [(0, 2050), (2050, 4099)]
     assert tmax0 == tmax1 == [11.0, 5.0] and tsum0 == tsum1 == [4099.0]
     assert np.array_equal(g0, g1) and np.array_equal(gw0, gw1)

@@ -87,6 +87,8 @@ def lib() -> C.CDLL:
     L.zc_search_select.argtypes = [vp, vp, i32, vp]
     L.zc_search_backprop.argtypes = [vp, vp, vp]
     L.zc_search_results.argtypes = [vp, vp, vp, vp, vp, i32, vp]
+    L.zc_search_results_begin.argtypes = [vp, vp]
+    L.zc_search_results_end.argtypes = [vp, vp]
     L.zc_search_tree_hash.argtypes = [vp, vp, vp]
     L.zc_search_get_counters.argtypes = [vp, vp, vp]
     L.zc_search_read_tree.argtypes = [vp, i32, vp, i64, vp, vp, vp]
@@ -110,6 +112,9 @@ def lib() -> C.CDLL:
     L.zc_tower_destroy.argtypes = [vp]
     L.zc_tower_destroy.restype = None
     L.zc_tower_forward.argtypes = [vp, vp, i32, vp, vp]
+    L.zc_tower_update_weights.argtypes = [vp, vp, vp, vp, C.c_float, vp]
+    L.zc_tower_fault.argtypes = [vp]
+    L.zc_tower_fault.restype = C.c_uint
     L.zc_tower_launches.argtypes = [vp]
     L.zc_tower_launches.restype = i64
     assert C.sizeof(RootResult) == ROOT_RESULT_DTYPE.itemsize == 48, (C.sizeof(RootResult), ROOT_RESULT_DTYPE.itemsize)

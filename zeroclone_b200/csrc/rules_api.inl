@@ -394,8 +394,18 @@ __device__ static int root_best_edge(const uint4* arena, int k, int ss) {
     return best;
 }
 
-__global__ void k_advance_c4(const uint4* __restrict__ arena_all, uint64_t arena_slots, int n, zc_c4_state* __restrict__ states,
-                             const uint8_t* __restrict__ active, int32_t* __restrict__ results, zc_chess_move* __restrict__ moves) {
+// what can go wrong for a tree in the self-play step; reported through err[0] (flags) and err[1] (lowest tree index)
+constexpr int ADV_ERR_OVERFLOW = 1;   // the tree outgrew its arena during the search: its move must not be played
+constexpr int ADV_ERR_NO_MOVE = 2;    // an active tree has no visited root child (no simulation ran, or a terminal root)
+constexpr int ADV_ERR_HISTORY = 4;    // chess: the side's move history is full (repetition detection would go stale)
+__device__ static void adv_report(int32_t* err, int flag, int tree) {
+    atomicOr(err, flag);
+    atomicMin(err + 1, tree);
+}
+
+__global__ void k_advance_c4(const uint4* __restrict__ arena_all, uint64_t arena_slots, const TreeCtl* __restrict__ ctl, int n,
+                             zc_c4_state* __restrict__ states, const uint8_t* __restrict__ active, int32_t* __restrict__ results,
+                             zc_chess_move* __restrict__ moves, int32_t* __restrict__ err) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n) return;
     zc_chess_move mv = {0, 0, 0, 0, 0.f};
@@ -404,7 +414,9 @@ __global__ void k_advance_c4(const uint4* __restrict__ arena_all, uint64_t arena
         const uint4* arena = arena_all + (uint64_t)t * arena_slots;
         const int k = (int)hdr_k(arena[0]);
         const int best = root_best_edge(arena, k, C4Game::SS);
-        if (best >= 0) {
+        if (ctl[t].status != 0) adv_report(err, ADV_ERR_OVERFLOW, t);
+        else if (best < 0) adv_report(err, ADV_ERR_NO_MOVE, t);
+        else {
             zc_c4_state s = states[t];
             c4::State r;
             r.cur = s.turn == 0 ? s.x : s.o;
@@ -446,11 +458,11 @@ __device__ static bool dev_repeated_prefix(const zc_chess_move* hist, int n, int
     return false;
 }
 
-__global__ void k_advance_chess(const uint4* __restrict__ arena_all, uint64_t arena_slots, int n,
+__global__ void k_advance_chess(const uint4* __restrict__ arena_all, uint64_t arena_slots, const TreeCtl* __restrict__ ctl, int n,
                                 zc_chess_state* __restrict__ states, const uint8_t* __restrict__ active,
                                 zc_chess_move* __restrict__ hist, int32_t* __restrict__ hist_len, int hist_cap,
                                 int* __restrict__ kmp_scratch, uint16_t* __restrict__ move_scratch,
-                                int32_t* __restrict__ results, zc_chess_move* __restrict__ moves) {
+                                int32_t* __restrict__ results, zc_chess_move* __restrict__ moves, int32_t* __restrict__ err) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n) return;
     zc_chess_move mv = {0, 0, 0, 0, 0.f};
@@ -459,7 +471,11 @@ __global__ void k_advance_chess(const uint4* __restrict__ arena_all, uint64_t ar
         const uint4* arena = arena_all + (uint64_t)t * arena_slots;
         const int k = (int)hdr_k(arena[0]);
         const int best = root_best_edge(arena, k, ChessGame::SS);
-        if (best >= 0) {
+        const int side = states[t].turn ? 1 : 0;
+        if (ctl[t].status != 0) adv_report(err, ADV_ERR_OVERFLOW, t);
+        else if (best < 0) adv_report(err, ADV_ERR_NO_MOVE, t);
+        else if (hist_len[t * 2 + side] >= hist_cap) adv_report(err, ADV_ERR_HISTORY, t);
+        else {
             const zc_chess_state s = states[t];
             const chess::Board b = ChessGame::load_state(arena + 1);
             const uint16_t m = ChessGame::move_at(arena, k, best);
@@ -480,8 +496,8 @@ __global__ void k_advance_chess(const uint4* __restrict__ arena_all, uint64_t ar
             zc_chess_move* hw = hist + ((size_t)t * 2 + 0) * hist_cap;
             zc_chess_move* hb = hist + ((size_t)t * 2 + 1) * hist_cap;
             int nw = hist_len[t * 2 + 0], nbk = hist_len[t * 2 + 1];
-            if (turn == 0) { if (nw < hist_cap) hw[nw++] = mv; hist_len[t * 2 + 0] = nw; }
-            else { if (nbk < hist_cap) hb[nbk++] = mv; hist_len[t * 2 + 1] = nbk; }
+            if (turn == 0) { hw[nw++] = mv; hist_len[t * 2 + 0] = nw; }      // room was checked above
+            else { hb[nbk++] = mv; hist_len[t * 2 + 1] = nbk; }
             // _evaluate(new state): check_win, then check_draw (:404-441)
             const int nturn = o.turn ? 1 : 0;
             const int nmoves = chess::generate(nb, nturn, move_scratch + (size_t)t * chess::MAX_PSEUDO);
@@ -511,10 +527,13 @@ extern "C" int zc_search_advance(zc_search* h, void* dev_states, const uint8_t* 
     if (!h->adv_res_dev) {
         CUDA_TRY(cudaMalloc((void**)&h->adv_res_dev, sizeof(int32_t) * (size_t)h->max_trees));
         CUDA_TRY(cudaMalloc((void**)&h->adv_mv_dev, sizeof(zc_chess_move) * (size_t)h->max_trees));
+        CUDA_TRY(cudaMalloc((void**)&h->adv_err_dev, sizeof(int32_t) * 2));
     }
+    const int32_t err0[2] = {0, 0x7FFFFFFF};
+    CUDA_TRY(cudaMemcpyAsync(h->adv_err_dev, err0, sizeof err0, cudaMemcpyHostToDevice, st));
     if (h->game == ZC_GAME_C4) {
-        k_advance_c4<<<(n + 127) / 128, 128, 0, st>>>(h->arena, h->arena_slots, n, (zc_c4_state*)dev_states, dev_active,
-                                                    h->adv_res_dev, h->adv_mv_dev);
+        k_advance_c4<<<(n + 127) / 128, 128, 0, st>>>(h->arena, h->arena_slots, h->ctl, n, (zc_c4_state*)dev_states, dev_active,
+                                                    h->adv_res_dev, h->adv_mv_dev, h->adv_err_dev);
     } else {
         if (!dev_hist || !dev_hist_len || hist_cap < 8) return fail(ZC_EINVAL, "advance: chess needs history buffers");
         if (h->adv_kmp_cap < hist_cap) {
@@ -523,15 +542,22 @@ extern "C" int zc_search_advance(zc_search* h, void* dev_states, const uint8_t* 
             CUDA_TRY(cudaMalloc((void**)&h->adv_kmp_dev, sizeof(int) * (size_t)h->max_trees * hist_cap));
             h->adv_kmp_cap = hist_cap;
         }
-        k_advance_chess<<<(n + 63) / 64, 64, 0, st>>>(h->arena, h->arena_slots, n, (zc_chess_state*)dev_states, dev_active,
+        k_advance_chess<<<(n + 63) / 64, 64, 0, st>>>(h->arena, h->arena_slots, h->ctl, n, (zc_chess_state*)dev_states, dev_active,
                                                     dev_hist, dev_hist_len, hist_cap, h->adv_kmp_dev, h->scratch,
-                                                    h->adv_res_dev, h->adv_mv_dev);
+                                                    h->adv_res_dev, h->adv_mv_dev, h->adv_err_dev);
     }
     h->launches++;
     CUDA_TRY(cudaGetLastError());
+    int32_t err[2] = {0, 0};
     CUDA_TRY(cudaMemcpyAsync(host_results, h->adv_res_dev, sizeof(int32_t) * (size_t)n, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaMemcpyAsync(host_moves, h->adv_mv_dev, sizeof(zc_chess_move) * (size_t)n, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(err, h->adv_err_dev, sizeof err, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
+    // never silent: a tree whose search was cut short, found no move, or whose history is full stays as it was
+    // (state unchanged, result ONGOING) and the call fails
+    if (err[0] & ADV_ERR_OVERFLOW) return fail(ZC_ECAPACITY, "advance: tree " + std::to_string(err[1]) + " outgrew its arena; its move was not played");
+    if (err[0] & ADV_ERR_HISTORY) return fail(ZC_ECAPACITY, "advance: move history of tree " + std::to_string(err[1]) + " is full (hist_cap); grow the history buffers");
+    if (err[0] & ADV_ERR_NO_MOVE) return fail(ZC_ESTATE, "advance: active tree " + std::to_string(err[1]) + " has no visited root move (no simulation ran or the root is terminal)");
     return ZC_OK;
 }
 

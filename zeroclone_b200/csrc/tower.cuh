@@ -16,7 +16,7 @@
 //     (dx = -1, 0, +1) therefore accumulate into three TMEM accumulators and the epilogue adds the
 //     dx = -1 (dx = +1) accumulator only to rows with x != 0 (x != W-1);
 //   - tcgen05.mma kind::f16 (bf16 x bf16 -> fp32), K = 16, issued by one elected thread from warp-uniform
-//     control flow; per layer and tile 9 taps x 8 k-steps.  CTAs run as PAIRS (cta_group::2, M = 256 over two
+//     control flow; per layer and tile 9 taps x 8 k-steps.  CTAs run as pairs (cta_group::2, M = 256 over two
 //     SMs): each CTA keeps its own 128-row tile and HALF of every tap's weights (64 of the 128 output
 //     channels), rank 0 issues for both -- the single-CTA form is bound by shared-memory bandwidth;
 //   - weights: one 16 KB image per (layer, tap, CTA rank) already in the shared-memory layout of the B operand,
@@ -28,7 +28,8 @@
 //     Two tiles per CTA alternate so the epilogue of one runs under the MMAs of the other; accumulators
 //     rotate through the 4 x 128 TMEM columns;
 //   - after the last block: per-row dot with the head weights, per-board sum in a fixed order, tanh;
-//   - every mbarrier wait is bounded: a protocol bug ends the kernel with an error instead of hanging the GPU.
+//   - every mbarrier wait is bounded (~2 s): a protocol bug ends the kernel with a fault word the host reports
+//     (zc_last_error names the wait) instead of hanging the GPU.
 #pragma once
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
@@ -46,7 +47,7 @@ constexpr int A_LBO = BUF_ROWS * 16;          // byte distance between k-chunks 
 constexpr int A_BUF_BYTES = KCHUNKS * A_LBO;  // 45056
 constexpr int B_LBO = CH * 16;                // weights: N = 128 rows of 16 B per k-chunk
 constexpr int W_TAP_BYTES = KCHUNKS * B_LBO;  // 32768
-constexpr int RING_BYTES = 4 * W_TAP_BYTES;    // weight ring: 4 stages of a whole tap, or 8 of the half a paired CTA holds
+constexpr int RING_BYTES = 4 * W_TAP_BYTES;    // weight ring: 8 stages of the half of a tap image a CTA of a pair holds
 constexpr int NT = 2;                         // tiles in flight per CTA
 constexpr int N_EPI_WARPS = 8;
 constexpr int N_THREADS = (2 + N_EPI_WARPS) * 32;
@@ -62,7 +63,6 @@ static_assert(SMEM_TOTAL <= 227 * 1024, "shared memory budget");
 
 struct Params {
     const __nv_bfloat16* planes;   // [n_leaves][CIN][H][W]
-    const uint8_t* wimg;           // [n_layers][9 taps][KCHUNKS][128][8] bf16, taps ordered (dx, dy)
     const uint8_t* wimg2;          // [n_layers][9 taps][2 halves of N][KCHUNKS][64][8]: what each CTA of a pair holds
     const float* bias;             // [n_layers][128] (BatchNorm folded)
     const float* head_w;           // [128]
@@ -70,7 +70,7 @@ struct Params {
     float* out;                    // [n_leaves]
     int n_leaves;
     int n_layers;                  // 1 + 2*blocks
-    unsigned int* fault;           // set when a barrier wait times out
+    unsigned int* fault;           // host-mapped word, set when a barrier wait times out (readable after the trap)
 };
 
 // ------------------------------------------------------------------------------------ PTX helpers
@@ -101,7 +101,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, unsigne
         if ((it & 1023u) == 1023u) {
             const long long now = clock64();
             if (t0 == 0) t0 = now;
-            else if (now - t0 > 20000000000ll) {   // ~10 s
+            else if (now - t0 > 4000000000ll) {    // ~2 s at 1.9 GHz; a whole launch takes milliseconds
                 atomicExch(fault, 0x80000000u | (unsigned)tag);
                 __threadfence_system();
                 __trap();
@@ -150,18 +150,6 @@ __device__ __forceinline__ uint32_t cluster_ctarank() {
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-// D[tmem] (+)= A[smem] * B[smem]^T, both K-major
-__device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
-        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
 __device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&v)[16]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
@@ -179,8 +167,7 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo, uint3
     return (uint64_t)((addr >> 4) & 0x3FFFu) | ((uint64_t)((lbo >> 4) & 0x3FFFu) << 16) |
            ((uint64_t)((sbo >> 4) & 0x3FFFu) << 32) | (1ull << 46);
 }
-// instruction descriptor (InstrDescriptor): c = f32, a = b = bf16, both K-major, N = 128, M = 128
-constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
+// instruction descriptor (InstrDescriptor): c = f32, a = b = bf16, both K-major, N = 128
 constexpr uint32_t IDESC2 = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) << 17) | ((256u >> 4) << 24);   // M = 256 over the pair
 
 // two fp32 lanes per instruction (FADD2 / FMUL2 / FFMA2): the epilogue's arithmetic in half the issue slots
@@ -230,15 +217,15 @@ using GeomC4 = Geom<6, 7, 3, 2>;      // c4_backend.py:52-61
 using GeomChess = Geom<8, 8, 2, 17>;  // chess_backend.cpp:461-521
 
 // ------------------------------------------------------------------------------------ the kernel
-template <class G, bool PAIR>
+template <class G>
 __global__ void __launch_bounds__(N_THREADS, 1) k_value_tower(const Params p) {
     extern __shared__ __align__(128) uint8_t smem[];
     const uint32_t sbase = smem_u32(smem);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // barriers
-    constexpr int NSTAGE = PAIR ? 8 : 4;
-    constexpr uint32_t STAGE_BYTES = RING_BYTES / NSTAGE;        // a whole tap image, or this CTA's half of it
-    constexpr uint32_t BLBO = PAIR ? B_LBO / 2 : B_LBO;          // k-chunk stride of the B operand held here
+    constexpr int NSTAGE = 8;
+    constexpr uint32_t STAGE_BYTES = RING_BYTES / NSTAGE;        // this CTA's half of a tap image
+    constexpr uint32_t BLBO = B_LBO / 2;                         // k-chunk stride of the B operand held here
     const uint32_t bar_wfull = sbase + SMEM_BARS, bar_wempty = bar_wfull + 8 * NSTAGE, bar_aready = bar_wempty + 8 * NSTAGE,
                    bar_accfull = bar_aready + 8 * NT, bar_pfree = bar_accfull + 8 * NT, bar_wpeer = bar_pfree + 8 * NT;
     uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + SMEM_BARS + 8 * (3 * NSTAGE + 3 * NT));
@@ -251,7 +238,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) k_value_tower(const Params p) {
     const int nj = cta < n_groups ? (n_groups - cta + grid - 1) / grid : 0;
     // groups per tile slot, padded to the longest CTA: the CTAs of a cluster share one weight stream
     const int ns = ((n_groups + grid - 1) / grid + NT - 1) / NT;
-    const uint32_t crank = PAIR ? cluster_ctarank() : 0u;   // 0 issues the pair's MMAs
+    const uint32_t crank = cluster_ctarank();               // 0 issues the pair's MMAs
     const int NL = p.n_layers;
     const int steps_per_slot = ns * NL;
 
@@ -267,26 +254,20 @@ __global__ void __launch_bounds__(N_THREADS, 1) k_value_tower(const Params p) {
             mbar_init(bar_wpeer + 8 * s, 1);      // pair: the other CTA's half of a stage has landed
         }
         for (int t = 0; t < NT; ++t) {
-            mbar_init(bar_aready + 8 * t, (PAIR ? 2 : 1) * N_EPI_WARPS);   // one arrival per epilogue warp; pair: both CTAs report to rank 0
+            mbar_init(bar_aready + 8 * t, 2 * N_EPI_WARPS);   // one arrival per epilogue warp; both CTAs report to rank 0
             mbar_init(bar_accfull + 8 * t, 1);
-            mbar_init(bar_pfree + 8 * t, (PAIR ? 2 : 1) * N_EPI_WARPS);    // side accumulators of a step have been read
+            mbar_init(bar_pfree + 8 * t, 2 * N_EPI_WARPS);    // side accumulators of a step have been read
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
-        if (PAIR) {
-            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "r"(512)
-                         : "memory");
-            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
-        } else {
-            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "r"(512)
-                         : "memory");
-            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-        }
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "r"(512)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
     }
     tc_fence_before();
     __syncthreads();
-    if (PAIR) cluster_sync();   // the peer's barriers and zeroed buffers exist before anything touches them
+    cluster_sync();   // the peer's barriers and zeroed buffers exist before anything touches them
     tc_fence_after();
     const uint32_t tmem = *tmem_ptr_smem;
 
@@ -302,8 +283,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) k_value_tower(const Params p) {
                         const uint32_t st = cnt % NSTAGE, ph = (cnt / NSTAGE) & 1u;
                         mbar_wait(bar_wempty + 8 * st, ph ^ 1u, p.fault, 1);
                         mbar_expect_tx(bar_wfull + 8 * st, bytes);
-                        const uint8_t* src = PAIR ? p.wimg2 + ((size_t)(layer * 9 + tap) * 2 + crank) * STAGE_BYTES
-                                                  : p.wimg + (size_t)(layer * 9 + tap) * STAGE_BYTES;
+                        const uint8_t* src = p.wimg2 + ((size_t)(layer * 9 + tap) * 2 + crank) * STAGE_BYTES;
                         bulk_g2s(sbase + SMEM_WRING + st * STAGE_BYTES, src, bytes, bar_wfull + 8 * st);
                     }
             }
@@ -316,7 +296,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) k_value_tower(const Params p) {
         asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(leader));
         const uint64_t desc_a_hi = smem_desc(0, A_LBO, 128), desc_b_hi = smem_desc(0, BLBO, 128);
         uint32_t wcnt = 0, gcnt = 0;
-        if (PAIR && crank != 0) {
+        if (crank != 0) {
             // the pair's second CTA issues nothing; it tells rank 0 when its half of each weight stage has landed
             const uint32_t total = (uint32_t)steps_per_slot * NT * 9u;
             for (; wcnt < total; ++wcnt) {
@@ -358,7 +338,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) k_value_tower(const Params p) {
                     for (int dyi = 0; dyi < 3; ++dyi, ++wcnt) {
                         const uint32_t st = wcnt % NSTAGE, ph = (wcnt / NSTAGE) & 1u;
                         mbar_wait(bar_wfull + 8 * st, ph, p.fault, 4);
-                        if (PAIR) mbar_wait(bar_wpeer + 8 * st, ph, p.fault, 7);
+                        mbar_wait(bar_wpeer + 8 * st, ph, p.fault, 7);
                         tc_fence_after();
                         const int shift = (dyi - 1) * G::RS + (g - 1);
                         const uint64_t ad = desc_a_hi | (uint64_t)(((abuf + shift * 16) >> 4) & 0x3FFFu);
@@ -366,25 +346,16 @@ __global__ void __launch_bounds__(N_THREADS, 1) k_value_tower(const Params p) {
                         if (leader) {
 #pragma unroll
                             for (int k = 0; k < CH / 16; ++k)
-                                if (k < ksteps) {
-                                    if (PAIR)
-                                        tc_mma2(acc, ad + (uint64_t)(k * (2 * A_LBO >> 4)), bd + (uint64_t)(k * (2 * BLBO >> 4)), IDESC2,
-                                                (uint32_t)((dyi | k) != 0));
-                                    else
-                                        tc_mma(acc, ad + (uint64_t)(k * (2 * A_LBO >> 4)), bd + (uint64_t)(k * (2 * BLBO >> 4)), IDESC,
-                                               (uint32_t)((dyi | k) != 0));
-                                }
-                            // stage reusable (in both CTAs of a pair) once these MMAs have read it
-                            if (PAIR) tc_commit2(bar_wempty + 8 * st);
-                            else tc_commit(bar_wempty + 8 * st);
+                                if (k < ksteps)
+                                    tc_mma2(acc, ad + (uint64_t)(k * (2 * A_LBO >> 4)), bd + (uint64_t)(k * (2 * BLBO >> 4)), IDESC2,
+                                            (uint32_t)((dyi | k) != 0));
+                            // stage reusable (in both CTAs of the pair) once these MMAs have read it
+                            tc_commit2(bar_wempty + 8 * st);
                         }
                         __syncwarp();
                     }
                 }
-                if (leader) {
-                    if (PAIR) tc_commit2(bar_accfull + 8 * slot);
-                    else tc_commit(bar_accfull + 8 * slot);
-                }
+                if (leader) tc_commit2(bar_accfull + 8 * slot);
                 __syncwarp();
             }
         }
@@ -426,12 +397,12 @@ __global__ void __launch_bounds__(N_THREADS, 1) k_value_tower(const Params p) {
         };
 
         // the MMA issuer (rank 0 of a pair) learns from both CTAs that a tile's input is in place
-        const uint32_t aready_dst = (PAIR && crank != 0) ? map_to_cta(bar_aready, 0) : bar_aready;
-        const uint32_t pfree_dst = (PAIR && crank != 0) ? map_to_cta(bar_pfree, 0) : bar_pfree;
+        const uint32_t aready_dst = crank != 0 ? map_to_cta(bar_aready, 0) : bar_aready;
+        const uint32_t pfree_dst = crank != 0 ? map_to_cta(bar_pfree, 0) : bar_pfree;
         auto signal = [&](uint32_t bar) {   // every lane has fenced its own accesses; one lane reports for the warp
             __syncwarp();
             if (lane == 0) {
-                if (PAIR && crank != 0) mbar_arrive_cluster(bar);
+                if (crank != 0) mbar_arrive_cluster(bar);
                 else mbar_arrive(bar);
             }
         };
@@ -542,11 +513,10 @@ __global__ void __launch_bounds__(N_THREADS, 1) k_value_tower(const Params p) {
 
     tc_fence_before();
     __syncthreads();
-    if (PAIR) cluster_sync();   // no CTA leaves while its peer may still use its shared memory, barriers or TMEM
+    cluster_sync();   // no CTA leaves while its peer may still use its shared memory, barriers or TMEM
     if (warp == 1) {
         tc_fence_after();
-        if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
-        else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
     }
 }
 

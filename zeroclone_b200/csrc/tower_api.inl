@@ -8,7 +8,11 @@ struct zc_tower {
     float* bias = nullptr;
     float* head_w = nullptr;
     float head_b = 0.f;
-    unsigned int* fault = nullptr;
+    unsigned int* fault = nullptr;       // device alias of fault_host
+    unsigned int* fault_host = nullptr;  // pinned + mapped: still readable after the kernel trapped
+    uint16_t* wstage = nullptr;          // pinned staging of the weight image (zc_tower_update_weights)
+    float* bstage = nullptr;             // pinned staging: biases, then head weights
+    size_t wimg_elems = 0;
     int n_sms = 0;
     int64_t launches = 0;
 };
@@ -19,6 +23,54 @@ static inline uint16_t f32_to_bf16_rne(float f) {
     if ((u & 0x7F800000u) == 0x7F800000u) return (uint16_t)((u >> 16) | ((u & 0xFFFFu) ? 0x40u : 0u));
     u += 0x7FFFu + ((u >> 16) & 1u);
     return (uint16_t)(u >> 16);
+}
+
+// Weight images in the shared-memory layout of the B operand, split by halves of N:
+// [layer][tap][n / 64][k-chunk][n % 64][8] bf16 -- the part each CTA of a cta_group::2 pair keeps in its own
+// shared memory; taps ordered by column offset first (dx = -1, 0, +1), then row offset (dy = -1, 0, +1).
+// conv_w is PyTorch's [Cout][Cin][kH][kW] per layer, stem first (cross-correlation: dy = kh-1, dx = kw-1).
+static void pack_tower_weights(const float* conv_w, int nl, int cin, uint16_t* img2) {
+    using namespace zc::tower;
+    memset(img2, 0, (size_t)nl * 9 * KCHUNKS * CH * 8 * sizeof(uint16_t));
+    size_t woff = 0;
+    for (int l = 0; l < nl; ++l) {
+        const int ci = l == 0 ? cin : CH;
+        for (int g = 0; g < 3; ++g)
+            for (int dyi = 0; dyi < 3; ++dyi) {
+                uint16_t* dst2 = img2 + ((size_t)l * 9 + g * 3 + dyi) * KCHUNKS * CH * 8;
+                for (int n = 0; n < CH; ++n)
+                    for (int k = 0; k < ci; ++k) {
+                        const uint16_t v = f32_to_bf16_rne(conv_w[woff + (((size_t)n * ci + k) * 3 + dyi) * 3 + g]);
+                        dst2[(((size_t)(n / 64) * KCHUNKS + k / 8) * 64 + n % 64) * 8 + (k % 8)] = v;
+                    }
+            }
+        woff += (size_t)CH * ci * 9;
+    }
+}
+
+// every live tower's fault word: a failed CUDA call anywhere in the library reports a tower protocol fault by name
+static std::vector<zc_tower*> g_towers;
+static const char* tower_wait_name(unsigned tag) {
+    switch (tag) {
+    case 1: return "weight producer waiting for a free ring stage";
+    case 2: return "MMA issuer waiting for a tile's input";
+    case 3: return "MMA issuer waiting for the side accumulators to be read";
+    case 4: return "MMA issuer waiting for a weight stage";
+    case 5: return "epilogue waiting for a full accumulator";
+    case 6: return "peer CTA waiting for its half of a weight stage";
+    case 7: return "MMA issuer waiting for the peer's half of a weight stage";
+    case 8: return "MMA issuer waiting for the centre accumulator to be read";
+    default: return "unknown wait";
+    }
+}
+static std::string tower_fault_note() {
+    std::string note;
+    for (zc_tower* t : g_towers) {
+        const unsigned f = t->fault_host ? *(volatile unsigned int*)t->fault_host : 0u;
+        if (f) note += " [k_value_tower fault on device " + std::to_string(t->device) + ": bounded wait timed out, tag " +
+                       std::to_string(f & 0xFFFFu) + " (" + tower_wait_name(f & 0xFFFFu) + ")]";
+    }
+    return note;
 }
 
 extern "C" int zc_tower_create(int game, int device, int n_blocks, const float* conv_w, const float* conv_b,
@@ -38,26 +90,8 @@ extern "C" int zc_tower_create(int game, int device, int n_blocks, const float* 
     using namespace zc::tower;
     const int cin = game == ZC_GAME_C4 ? GeomC4::CIN : GeomChess::CIN;
     const int nl = 1 + 2 * n_blocks;
-    // weight images in the shared-memory layout of the B operand, split by halves of N:
-    // [layer][tap][n / 64][k-chunk][n % 64][8] bf16 -- the part each CTA of a cta_group::2 pair keeps in its own
-    // shared memory; taps ordered by column offset first (dx = -1, 0, +1), then row offset (dy = -1, 0, +1).
-    // conv_w is PyTorch's [Cout][Cin][kH][kW] per layer, stem first (cross-correlation: dy = kh-1, dx = kw-1).
-    std::vector<uint16_t> img2((size_t)nl * 9 * KCHUNKS * CH * 8, 0);
-    size_t woff = 0;
-    for (int l = 0; l < nl; ++l) {
-        const int ci = l == 0 ? cin : CH;
-        for (int g = 0; g < 3; ++g)
-            for (int dyi = 0; dyi < 3; ++dyi) {
-                uint16_t* dst2 = img2.data() + ((size_t)l * 9 + g * 3 + dyi) * KCHUNKS * CH * 8;
-                for (int n = 0; n < CH; ++n)
-                    for (int k = 0; k < ci; ++k) {
-                        const uint16_t v = f32_to_bf16_rne(conv_w[woff + (((size_t)n * ci + k) * 3 + dyi) * 3 + g]);
-                        dst2[(((size_t)(n / 64) * KCHUNKS + k / 8) * 64 + n % 64) * 8 + (k % 8)] = v;
-                    }
-            }
-        woff += (size_t)CH * ci * 9;
-    }
     zc_tower* t = new zc_tower;
+    t->wimg_elems = (size_t)nl * 9 * KCHUNKS * CH * 8;
     t->game = game;
     t->device = device;
     t->n_layers = nl;
@@ -65,7 +99,8 @@ extern "C" int zc_tower_create(int game, int device, int n_blocks, const float* 
     t->head_b = head_b;
     t->n_sms = prop.multiProcessorCount;
     auto cleanup = [&](int rc) {
-        cudaFree(t->wimg2); cudaFree(t->bias); cudaFree(t->head_w); cudaFree(t->fault);
+        cudaFree(t->wimg2); cudaFree(t->bias); cudaFree(t->head_w);
+        cudaFreeHost(t->fault_host); cudaFreeHost(t->wstage); cudaFreeHost(t->bstage);
         delete t;
         return rc;
     };
@@ -74,19 +109,48 @@ extern "C" int zc_tower_create(int game, int device, int n_blocks, const float* 
         cudaError_t _e = (expr);                                                                           \
         if (_e != cudaSuccess) return cleanup(fail(ZC_ECUDA, std::string(#expr) + ": " + cudaGetErrorString(_e))); \
     } while (0)
-    TOWER_TRY(cudaMalloc(&t->wimg2, img2.size() * 2));
+    TOWER_TRY(cudaMalloc(&t->wimg2, t->wimg_elems * 2));
     TOWER_TRY(cudaMalloc(&t->bias, sizeof(float) * nl * CH));
     TOWER_TRY(cudaMalloc(&t->head_w, sizeof(float) * CH));
-    TOWER_TRY(cudaMalloc(&t->fault, sizeof(unsigned int)));
-    TOWER_TRY(cudaMemcpy(t->wimg2, img2.data(), img2.size() * 2, cudaMemcpyHostToDevice));
-    TOWER_TRY(cudaMemcpy(t->bias, conv_b, sizeof(float) * nl * CH, cudaMemcpyHostToDevice));
-    TOWER_TRY(cudaMemcpy(t->head_w, head_w, sizeof(float) * CH, cudaMemcpyHostToDevice));
-    TOWER_TRY(cudaMemset(t->fault, 0, sizeof(unsigned int)));
-    TOWER_TRY(cudaFuncSetAttribute(k_value_tower<GeomC4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
-    TOWER_TRY(cudaFuncSetAttribute(k_value_tower<GeomChess, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
+    TOWER_TRY(cudaHostAlloc(&t->fault_host, sizeof(unsigned int), cudaHostAllocMapped));
+    *t->fault_host = 0u;
+    TOWER_TRY(cudaHostGetDevicePointer(&t->fault, t->fault_host, 0));
+    TOWER_TRY(cudaMallocHost(&t->wstage, t->wimg_elems * 2));
+    TOWER_TRY(cudaMallocHost(&t->bstage, sizeof(float) * (nl + 1) * CH));
+    TOWER_TRY(cudaFuncSetAttribute(k_value_tower<GeomC4>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
+    TOWER_TRY(cudaFuncSetAttribute(k_value_tower<GeomChess>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
 #undef TOWER_TRY
+    if (int rc = zc_tower_update_weights(t, conv_w, conv_b, head_w, head_b, nullptr)) return cleanup(rc);
+    if (cudaStreamSynchronize(nullptr) != cudaSuccess) return cleanup(fail(ZC_ECUDA, "zc_tower_create: weight upload failed"));
+    g_towers.push_back(t);
     *out = t;
     return ZC_OK;
+}
+
+extern "C" int zc_tower_update_weights(zc_tower* t, const float* conv_w, const float* conv_b, const float* head_w, float head_b,
+                                       void* stream) {
+    if (!t) return fail(ZC_EINVAL, "tower handle is NULL");
+    if (!conv_w || !conv_b || !head_w) return fail(ZC_EINVAL, "bad tower arguments");
+    using namespace zc::tower;
+    CUDA_TRY(cudaSetDevice(t->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    // the staging buffers may still feed the previous update's copies, and no forward may read half-new weights
+    CUDA_TRY(cudaDeviceSynchronize());
+    pack_tower_weights(conv_w, t->n_layers, t->cin, t->wstage);
+    memcpy(t->bstage, conv_b, sizeof(float) * t->n_layers * CH);
+    memcpy(t->bstage + (size_t)t->n_layers * CH, head_w, sizeof(float) * CH);
+    t->head_b = head_b;
+    CUDA_TRY(cudaMemcpyAsync(t->wimg2, t->wstage, t->wimg_elems * 2, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(t->bias, t->bstage, sizeof(float) * t->n_layers * CH, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(t->head_w, t->bstage + (size_t)t->n_layers * CH, sizeof(float) * CH, cudaMemcpyHostToDevice, st));
+    return ZC_OK;
+}
+
+extern "C" unsigned int zc_tower_fault(zc_tower* t) {
+    if (!t || !t->fault_host) return 0u;
+    const unsigned f = *(volatile unsigned int*)t->fault_host;
+    *t->fault_host = 0u;
+    return f;
 }
 
 extern "C" void zc_tower_destroy(zc_tower* t) {
@@ -95,7 +159,10 @@ extern "C" void zc_tower_destroy(zc_tower* t) {
     cudaFree(t->wimg2);
     cudaFree(t->bias);
     cudaFree(t->head_w);
-    cudaFree(t->fault);
+    cudaFreeHost(t->fault_host);
+    cudaFreeHost(t->wstage);
+    cudaFreeHost(t->bstage);
+    g_towers.erase(std::remove(g_towers.begin(), g_towers.end(), t), g_towers.end());
     delete t;
 }
 
@@ -107,7 +174,6 @@ extern "C" int zc_tower_forward(zc_tower* t, const void* dev_planes_bf16, int n_
     CUDA_TRY(cudaSetDevice(t->device));
     Params p;
     p.planes = reinterpret_cast<const __nv_bfloat16*>(dev_planes_bf16);
-    p.wimg = nullptr;      // the single-CTA layout is not instantiated
     p.wimg2 = t->wimg2;
     p.bias = t->bias;
     p.head_w = t->head_w;
@@ -135,7 +201,7 @@ extern "C" int zc_tower_forward(zc_tower* t, const void* dev_planes_bf16, int n_
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     const bool c4 = t->game == ZC_GAME_C4;
-    void (*kern)(const Params) = c4 ? k_value_tower<GeomC4, true> : k_value_tower<GeomChess, true>;
+    void (*kern)(const Params) = c4 ? k_value_tower<GeomC4> : k_value_tower<GeomChess>;
     CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, p));
     ++t->launches;
     return ZC_OK;

@@ -28,8 +28,9 @@ static const uint8_t kDefaultOrder[128][8] = {
 using namespace zc;
 
 static thread_local std::string g_err;
+static std::string tower_fault_note();   // tower_api.inl: names a tower kernel's timed-out wait, if any
 static int fail(int code, const std::string& msg) {
-    g_err = msg;
+    g_err = code == ZC_ECUDA ? msg + tower_fault_note() : msg;
     return code;
 }
 #define CUDA_TRY(expr)                                                                         \
@@ -52,7 +53,11 @@ struct zc_search {
     uint16_t* scratch = nullptr;        // chess move staging, one buffer per lane
     void* roots_dev = nullptr;          // staging for host roots
     zc_root_result* res_dev = nullptr;
+    zc_root_result* res_dev2[2] = {nullptr, nullptr};   // results_begin/end: double-buffered device results
     zc_root_result* res_host = nullptr;  // pinned staging of the per-tree results
+    cudaStream_t copy_stream = nullptr;  // results_begin: the D2H copy runs beside the next step's kernels
+    cudaEvent_t ev_res_ready = nullptr, ev_copy_done[2] = {nullptr, nullptr};
+    int res_flip = 0, res_pending = -1, res_pending_n = 0;
     int32_t* visits_dev = nullptr;
     double* wsum_dev = nullptr;
     zc_chess_move* moves_dev = nullptr;
@@ -62,6 +67,7 @@ struct zc_search {
     zc_chess_move* adv_mv_dev = nullptr;
     int* adv_kmp_dev = nullptr;
     int adv_kmp_cap = 0;
+    int32_t* adv_err_dev = nullptr;     // {flags, first offending tree}
     int64_t bytes = 0;
     int64_t launches = 0;
     int fused_grid = 0;
@@ -344,13 +350,23 @@ extern "C" int zc_search_create(int game, int device, int max_trees, int max_sim
         volatile double x = (double)i;
         lt[i] = std::log(x);
     }
-    CUDA_TRY(cudaMemcpy(h->log_tab, lt.data(), lt.size() * sizeof(double), cudaMemcpyHostToDevice));
     int occ = 0, sms = 0;
-    if (game == ZC_GAME_C4)
-        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_search_fused<C4Game>, SEARCH_BLOCK, 0));
-    else
-        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_search_fused<ChessGame>, SEARCH_BLOCK, 0));
-    CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    e = cudaMemcpy(h->log_tab, lt.data(), lt.size() * sizeof(double), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess)
+        e = game == ZC_GAME_C4 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_search_fused<C4Game>, SEARCH_BLOCK, 0)
+                               : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_search_fused<ChessGame>, SEARCH_BLOCK, 0);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_res_ready, cudaEventDisableTiming);
+    for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
+        e = cudaEventCreateWithFlags(&h->ev_copy_done[i], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = alloc((void**)&h->res_dev2[i], sizeof(zc_root_result) * max_trees);
+    }
+    if (e != cudaSuccess) {     // the handle is not handed out: free what it holds
+        std::string msg = std::string("zc_search_create: ") + cudaGetErrorString(e);
+        zc_search_destroy(h);
+        return fail(ZC_ECUDA, msg);
+    }
     h->fused_grid = occ * sms;
     if (game == ZC_GAME_CHESS) {
         const size_t warps = (size_t)std::max(max_trees, h->fused_grid * (SEARCH_BLOCK / 32));
@@ -378,7 +394,14 @@ extern "C" int zc_search_destroy(zc_search* h) {
     cudaFree(h->scratch);
     cudaFree(h->roots_dev);
     cudaFree(h->res_dev);
+    cudaFree(h->res_dev2[0]);
+    cudaFree(h->res_dev2[1]);
     cudaFreeHost(h->res_host);
+    if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+    if (h->ev_res_ready) cudaEventDestroy(h->ev_res_ready);
+    if (h->ev_copy_done[0]) cudaEventDestroy(h->ev_copy_done[0]);
+    if (h->ev_copy_done[1]) cudaEventDestroy(h->ev_copy_done[1]);
+    cudaFree(h->adv_err_dev);
     cudaFree(h->visits_dev);
     cudaFree(h->wsum_dev);
     cudaFree(h->moves_dev);
@@ -417,9 +440,9 @@ extern "C" int zc_search_set_roots(zc_search* h, const void* host_states, int n,
     cudaStream_t st = (cudaStream_t)stream;
     const size_t sz = h->game == ZC_GAME_C4 ? sizeof(zc_c4_state) : sizeof(zc_chess_state);
     CUDA_TRY(cudaMemcpyAsync(h->roots_dev, host_states, sz * n, cudaMemcpyHostToDevice, st));
-    if (int rc = set_roots_common(h, h->roots_dev, n, st)) return rc;
-    CUDA_TRY(cudaStreamSynchronize(st));
-    return ZC_OK;
+    // stream-ordered, no host synchronisation: cudaMemcpyAsync has staged a pageable source before it returns;
+    // a pinned source must stay unchanged until the stream has passed this point
+    return set_roots_common(h, h->roots_dev, n, st);
 }
 
 extern "C" int zc_search_set_roots_dev(zc_search* h, const void* dev_states, int n, void* stream) {
@@ -536,6 +559,16 @@ extern "C" int zc_search_backprop(zc_search* h, const float* dev_values, void* s
     return ZC_OK;
 }
 
+static void launch_results_kernel(zc_search* h, zc_root_result* dst, int32_t* visits, double* wsum, zc_chess_move* moves, int stride,
+                                  cudaStream_t st) {
+    const int n = h->n_trees;
+    if (h->game == ZC_GAME_C4)
+        k_results_c4<<<(n + 127) / 128, 128, 0, st>>>(h->arena, h->arena_slots, h->ctl, n, dst, visits, wsum, moves, stride);
+    else
+        k_results_chess<<<(n + 127) / 128, 128, 0, st>>>(h->arena, h->arena_slots, h->ctl, n, dst, visits, wsum, moves, stride);
+    h->launches++;
+}
+
 extern "C" int zc_search_results(zc_search* h, zc_root_result* results, int32_t* visits, double* value_sums,
                                  zc_chess_move* moves, int stride, void* stream) {
     if (int rc = check_handle(h)) return rc;
@@ -560,21 +593,50 @@ extern "C" int zc_search_results(zc_search* h, zc_root_result* results, int32_t*
         CUDA_TRY(cudaMemsetAsync(h->wsum_dev, 0, sizeof(double) * (size_t)n * stride, st));
         CUDA_TRY(cudaMemsetAsync(h->moves_dev, 0, sizeof(zc_chess_move) * (size_t)n * stride, st));
     }
-    if (h->game == ZC_GAME_C4)
-        k_results_c4<<<(n + 127) / 128, 128, 0, st>>>(h->arena, h->arena_slots, h->ctl, n, h->res_dev,
-                                                    visits ? h->visits_dev : nullptr, value_sums ? h->wsum_dev : nullptr,
-                                                    moves ? h->moves_dev : nullptr, stride);
-    else
-        k_results_chess<<<(n + 127) / 128, 128, 0, st>>>(h->arena, h->arena_slots, h->ctl, n, h->res_dev,
-                                                       visits ? h->visits_dev : nullptr, value_sums ? h->wsum_dev : nullptr,
-                                                       moves ? h->moves_dev : nullptr, stride);
-    h->launches++;
+    launch_results_kernel(h, h->res_dev, visits ? h->visits_dev : nullptr, value_sums ? h->wsum_dev : nullptr,
+                          moves ? h->moves_dev : nullptr, stride, st);
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaMemcpyAsync(h->res_host, h->res_dev, sizeof(zc_root_result) * n, cudaMemcpyDeviceToHost, st));
     if (visits) CUDA_TRY(cudaMemcpyAsync(visits, h->visits_dev, sizeof(int32_t) * (size_t)n * stride, cudaMemcpyDeviceToHost, st));
     if (value_sums) CUDA_TRY(cudaMemcpyAsync(value_sums, h->wsum_dev, sizeof(double) * (size_t)n * stride, cudaMemcpyDeviceToHost, st));
     if (moves) CUDA_TRY(cudaMemcpyAsync(moves, h->moves_dev, sizeof(zc_chess_move) * (size_t)n * stride, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
+    memcpy(results, h->res_host, sizeof(zc_root_result) * (size_t)n);
+    for (int i = 0; i < n; ++i)
+        if (results[i].status != 0) return fail(ZC_ECAPACITY, "tree " + std::to_string(i) + " outgrew its arena");
+    return ZC_OK;
+}
+
+// Root readout without stalling the host: the per-tree results (mcts.cpp:150-159) are computed on `stream`, copied
+// to pinned host memory on the handle's copy stream, and collected by zc_search_results_end.  The next
+// set_roots / run may be enqueued at once; device results are double-buffered.
+extern "C" int zc_search_results_begin(zc_search* h, void* stream) {
+    if (int rc = check_handle(h)) return rc;
+    if (h->n_trees < 1) return fail(ZC_ESTATE, "no roots set");
+    CUDA_TRY(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int f = h->res_flip;
+    CUDA_TRY(cudaStreamWaitEvent(st, h->ev_copy_done[f], 0));      // the copy that last read this buffer (two begins ago)
+    launch_results_kernel(h, h->res_dev2[f], nullptr, nullptr, nullptr, 0, st);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaEventRecord(h->ev_res_ready, st));
+    CUDA_TRY(cudaStreamWaitEvent(h->copy_stream, h->ev_res_ready, 0));
+    CUDA_TRY(cudaMemcpyAsync(h->res_host, h->res_dev2[f], sizeof(zc_root_result) * (size_t)h->n_trees, cudaMemcpyDeviceToHost, h->copy_stream));
+    CUDA_TRY(cudaEventRecord(h->ev_copy_done[f], h->copy_stream));
+    h->res_pending = f;
+    h->res_pending_n = h->n_trees;
+    h->res_flip ^= 1;
+    return ZC_OK;
+}
+
+extern "C" int zc_search_results_end(zc_search* h, zc_root_result* results) {
+    if (int rc = check_handle(h)) return rc;
+    if (!results) return fail(ZC_EINVAL, "results is NULL");
+    if (h->res_pending < 0) return fail(ZC_ESTATE, "results_end without results_begin");
+    CUDA_TRY(cudaSetDevice(h->device));
+    CUDA_TRY(cudaEventSynchronize(h->ev_copy_done[h->res_pending]));
+    const int n = h->res_pending_n;
+    h->res_pending = -1;
     memcpy(results, h->res_host, sizeof(zc_root_result) * (size_t)n);
     for (int i = 0; i < n; ++i)
         if (results[i].status != 0) return fail(ZC_ECAPACITY, "tree " + std::to_string(i) + " outgrew its arena");

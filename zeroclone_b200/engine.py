@@ -9,6 +9,7 @@ Result convention (engine.py:148-153): +1 first player / white won, -1 second / 
 from __future__ import annotations
 
 import importlib
+import threading
 from dataclasses import dataclass, field
 from typing import Any, Callable, Optional, Sequence
 
@@ -48,14 +49,18 @@ class Engine:
         self.threads = self.config.get("threads", 1)
         self.batch_size = int(self.config.get("mcts", {}).get("batch_size", 32))   # extra key; reference default 32
         self.last_search: dict = {}
+        # the REST server calls these methods from a thread pool: game bookkeeping and the shared device search
+        # handle are used by one request at a time (the reference searched a private tree per request)
+        self._lock = threading.RLock()
         self.reset_all_games()
 
     # ------------------------------------------------------------------ bookkeeping
     def add_game(self, init_state=None):
         state = init_state or self.backend.create_init_state()
-        self.states.append(state)
-        self.history.append(History(states=[state], result=None))
-        return len(self.states) - 1
+        with self._lock:
+            self.states.append(state)
+            self.history.append(History(states=[state], result=None))
+            return len(self.states) - 1
 
     def get_state(self, idx=0):
         return self.states[idx]
@@ -91,14 +96,15 @@ class Engine:
         return self.backend.get_legal_moves(self.states[idx])
 
     def play_move(self, move, idx=0):
-        if not self._is_legal(move, idx):
-            raise ValueError("Illegal move")
-        nxt = self.backend.play_move(self.states[idx], move)
-        self.states[idx] = nxt
-        h = self.history[idx]
-        h.states.append(nxt)
-        h.result = self._evaluate(nxt)
-        return h.result
+        with self._lock:
+            if not self._is_legal(move, idx):
+                raise ValueError("Illegal move")
+            nxt = self.backend.play_move(self.states[idx], move)
+            self.states[idx] = nxt
+            h = self.history[idx]
+            h.states.append(nxt)
+            h.result = self._evaluate(nxt)
+            return h.result
 
     def play_moves_parallel(self, moves, max_workers=None):
         return {idx: self.play_move(mv, idx) for idx, mv in moves.items()}
@@ -109,6 +115,10 @@ class Engine:
     def play_mcts_parallel(self, idxs, simulations=1000, c=1.4, max_workers=None):
         """For every listed game: root terminal guard, search, apply the chosen move
         (engine.py:119-129), with all searches in one batch on the GPU."""
+        with self._lock:
+            return self._play_mcts_parallel(idxs, simulations, c)
+
+    def _play_mcts_parallel(self, idxs, simulations, c):
         results: dict = {}
         todo = {0: [], 1: []}
         for idx in idxs:

@@ -96,8 +96,6 @@ class FusedTowerEvaluator:
     def __init__(self, model: nn.Module, device="cuda", dtype: torch.dtype = torch.bfloat16):
         import ctypes as C
 
-        import numpy as np
-
         from . import _ffi
 
         if dtype != torch.bfloat16:
@@ -110,6 +108,20 @@ class FusedTowerEvaluator:
         game = {2: _ffi.GAME_C4, 17: _ffi.GAME_CHESS}.get(self.in_planes)
         if game is None or model.stem[0].out_channels != 128:
             raise ValueError("fused tower supports the 128-channel tower on Connect Four (2 planes) or chess (17 planes)")
+        self.n_blocks = len(model.res)
+        conv_w, conv_b, head_w, head_b = self._folded(model)
+        self._h = C.c_void_p()
+        index = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        self._index = index
+        _ffi.check(_ffi.lib().zc_tower_create(game, index, self.n_blocks, conv_w.ctypes.data_as(C.c_void_p),
+                                              conv_b.ctypes.data_as(C.c_void_p), head_w.ctypes.data_as(C.c_void_p),
+                                              head_b, C.byref(self._h)))
+
+    @staticmethod
+    def _folded(model: nn.Module):
+        """BatchNorm (eval mode) folded into every convolution in fp32: the plain float arrays zc_tower_create takes"""
+        import numpy as np
+
         ws, bs = [], []
         w, b = _fold(model.stem[0], model.stem[1])
         ws.append(w.reshape(-1))
@@ -123,12 +135,21 @@ class FusedTowerEvaluator:
         conv_b = np.ascontiguousarray(torch.cat(bs).cpu().numpy(), dtype=np.float32)
         lin = model.head[2]
         head_w = np.ascontiguousarray(lin.weight.detach().float().view(-1).cpu().numpy(), dtype=np.float32)
-        self._h = C.c_void_p()
-        index = self.device.index if self.device.index is not None else torch.cuda.current_device()
-        self._index = index
-        _ffi.check(_ffi.lib().zc_tower_create(game, index, len(model.res), conv_w.ctypes.data_as(C.c_void_p),
-                                              conv_b.ctypes.data_as(C.c_void_p), head_w.ctypes.data_as(C.c_void_p),
-                                              float(lin.bias.detach().float().item()), C.byref(self._h)))
+        return conv_w, conv_b, head_w, float(lin.bias.detach().float().item())
+
+    def update_weights(self, model: nn.Module) -> None:
+        """Freshly trained weights into the resident tower (zc_tower_update_weights): what the training loop does
+        between cycles instead of rebuilding the evaluator (scripts/train.py:143-146 + value_functions.py:104-112)."""
+        import ctypes as C
+
+        from . import _ffi
+
+        if len(model.res) != self.n_blocks or model.stem[0].in_channels != self.in_planes:
+            raise ValueError("update_weights: the model's architecture differs from the tower's")
+        conv_w, conv_b, head_w, head_b = self._folded(model)
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        _ffi.check(_ffi.lib().zc_tower_update_weights(self._h, conv_w.ctypes.data_as(C.c_void_p), conv_b.ctypes.data_as(C.c_void_p),
+                                                      head_w.ctypes.data_as(C.c_void_p), head_b, C.c_void_p(stream)))
 
     def close(self) -> None:
         from . import _ffi

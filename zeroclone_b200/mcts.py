@@ -7,6 +7,7 @@ raises TypeError -- there is deliberately no CPU search to fall back to.
 """
 from __future__ import annotations
 
+import threading
 from typing import Dict, Sequence, Tuple
 
 import numpy as np
@@ -15,29 +16,64 @@ from . import _ffi
 from .search import TreeSearch
 
 _POOL: Dict[Tuple[int, int], TreeSearch] = {}
+_POOL_LOCK = threading.RLock()
+_KEY_LOCKS: Dict[Tuple[int, int], threading.RLock] = {}
 
 
-def searcher(game: int, n_trees: int, sims: int, device: int | None = None) -> TreeSearch:
-    """A TreeSearch handle with room for n_trees x sims on `device`, grown geometrically."""
+def _key(game: int, device: int | None) -> Tuple[int, int]:
     if device is None:
         import torch
         device = torch.cuda.current_device() if torch.cuda.is_available() else 0
-    key = (game, device)
-    ts = _POOL.get(key)
-    if ts is None or ts.max_trees < n_trees or ts.max_sims < sims:
-        cap_t = max(n_trees, 2 * ts.max_trees if ts and ts.max_trees < n_trees else 0, 1)
+    return game, device
+
+
+def device_lock(game: int, device: int | None = None) -> threading.RLock:
+    """One lock per pooled handle.  A search is set_roots -> run -> results on ONE shared handle (and one shared
+    network evaluator); callers that may run concurrently -- the REST server's threadpool, ctypes calls release the
+    GIL -- hold this lock for the whole sequence, or a game would receive a move computed for another game's root.
+    (The reference built a private tree per request, mcts.cpp:104-109.)"""
+    key = _key(game, device)
+    with _POOL_LOCK:
+        return _KEY_LOCKS.setdefault(key, threading.RLock())
+
+
+def searcher(game: int, n_trees: int, sims: int, device: int | None = None) -> TreeSearch:
+    """A TreeSearch handle with room for n_trees x sims on `device`; capacities only ever grow (trees
+    geometrically).  A failed growth leaves the pool consistent: the old handle stays if the new one cannot be
+    created next to it; if memory is the problem the old one is released first and, should the retry fail too,
+    the pool entry is dropped so the next call starts clean."""
+    key = _key(game, device)
+    with _POOL_LOCK:
+        ts = _POOL.get(key)
+        if ts is not None and ts.max_trees >= n_trees and ts.max_sims >= sims:
+            return ts
+        if ts is None:
+            cap_t = max(n_trees, 1)
+        elif n_trees > ts.max_trees:
+            cap_t = max(n_trees, 2 * ts.max_trees)
+        else:
+            cap_t = ts.max_trees                 # only `sims` grew: keep the tree capacity
         cap_s = max(sims, ts.max_sims if ts else 0, 32)
-        if ts is not None:
-            ts.close()
-        ts = TreeSearch(game, cap_t, cap_s, device=device)
-        _POOL[key] = ts
-    return ts
+        try:
+            new = TreeSearch(game, cap_t, cap_s, device=key[1])
+        except _ffi.ZcError:
+            if ts is None:
+                raise
+            ts.close()                       # make room and try once more, at the size actually asked for
+            del _POOL[key]
+            new = TreeSearch(game, max(n_trees, 1), max(sims, 32), device=key[1])
+        else:
+            if ts is not None:
+                ts.close()
+        _POOL[key] = new
+        return new
 
 
 def release_all() -> None:
-    for ts in _POOL.values():
-        ts.close()
-    _POOL.clear()
+    with _POOL_LOCK:
+        for ts in _POOL.values():
+            ts.close()
+        _POOL.clear()
 
 
 def _device_pieces(value, policy, backend):
@@ -62,14 +98,17 @@ def search_batch(states: Sequence, value, policy, backend, simulations: int, c: 
         roots[i] = backend.pack_state(s)
     if seed is None:
         seed = int(np.random.SeedSequence().generate_state(1, dtype=np.uint64)[0])
-    ts = searcher(game, n, simulations)
-    ts.set_roots(roots)
-    ts.set_policy_freedom(getattr(policy, "device_freedom", 0.0))
-    if kind == "builtin":
-        ts.run(simulations, c, batch_size, ev, pol, seed)
-    else:
-        ts.run_network(ev, simulations, c, batch_size, pol, seed)
-    out = ts.results(stats=stats)
+    if simulations < 1:
+        raise ValueError("simulations must be >= 1")
+    with device_lock(game):
+        ts = searcher(game, n, simulations)
+        ts.set_roots(roots)
+        ts.set_policy_freedom(getattr(policy, "device_freedom", 0.0))
+        if kind == "builtin":
+            ts.run(simulations, c, batch_size, ev, pol, seed)
+        else:
+            ts.run_network(ev, simulations, c, batch_size, pol, seed)
+        out = ts.results(stats=stats)
     res = out["result"]
     if game == _ffi.GAME_C4:
         out["moves_out"] = [backend.move_from_result(r["best_move"]) if r["best"] >= 0 else None for r in res]

@@ -8,4 +8,4 @@ class ValueNetwork(ValueTower):
 
 
 def add_safe_globals():
-    safe_globals(ValueNetwork)
+    safe_globals(ValueNetwork, reference_module="models.chess_value.network")

@@ -9,4 +9,4 @@ class ValueNetwork(ValueTower):
 
 
 def add_safe_globals():
-    safe_globals(ValueNetwork)
+    safe_globals(ValueNetwork, reference_module="models.connect4_value.network")

@@ -64,10 +64,17 @@ class ValueNetDataset(Dataset):
         return self.states[i], self.values[i]
 
 
-def safe_globals(*extra) -> None:
-    """register what torch.load(weights_only=True) must be allowed to unpickle for a whole-module checkpoint"""
+def safe_globals(*extra, reference_module: Optional[str] = None) -> None:
+    """Register what torch.load(weights_only=True) must be allowed to unpickle for a whole-module checkpoint
+    (the reference does the same so that the safe loader works, network.py:59-72).  `reference_module`: the path
+    the REFERENCE pickles these classes under (e.g. "models.chess_value.network"), so checkpoints written by the
+    reference load here too; the names resolve to this package's classes through the repo-root import aliases."""
     layers = (nn.Sequential, nn.Conv2d, nn.BatchNorm2d, nn.ReLU, nn.AdaptiveAvgPool2d, nn.Flatten, nn.Linear, nn.Tanh)
-    torch.serialization.add_safe_globals([ValueTower, ResidualBlock, *layers, *extra])
+    allowed = [ValueTower, ResidualBlock, *layers, *extra]
+    if reference_module:
+        allowed += [(ResidualBlock, f"{reference_module}.ResidualBlock")]
+        allowed += [(cls, f"{reference_module}.{cls.__name__}") for cls in extra]
+    torch.serialization.add_safe_globals(allowed)
 
 
 def _one_epoch(model, batches: Iterable, optimiser, device, grad_sync: Optional[Callable]) -> float:

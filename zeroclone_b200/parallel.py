@@ -75,33 +75,93 @@ def gather_objects(obj):
 
 
 class GradSync:
-    """Data-parallel gradient averaging for the value-network training step: one flat bucket
-    (2,383,361 fp32 gradients = 9.53 MB for the 128x8 tower), one all-reduce (NCCL over
-    NVLink/NVSwitch on GPUs), then divide by the world size.  Optionally weights each rank's
-    gradient by its sample count so that uneven self-play shards average correctly."""
+    """Data-parallel gradient averaging for the value-network training step: ONE flat bucket, ONE all-reduce per
+    step (NCCL over NVLink/NVSwitch on GPUs) -- 2,383,361 fp32 gradients + 1 sample count = 9.53 MB for the
+    128x8 tower.  Every parameter's `.grad` is a view into the bucket, so nothing is copied in or out; each rank's
+    gradient is weighted by its sample count (the count rides in the bucket's last element), so uneven self-play
+    shards -- including empty ones -- average correctly.  Keep the views alive: `optimizer.zero_grad(set_to_none=False)`
+    (or `sync.zero_()`).  `timed=True` brackets the collective with CUDA events; `allreduce_ms()` reads them back."""
 
-    def __init__(self, model: torch.nn.Module):
+    def __init__(self, model: torch.nn.Module, timed: bool = False):
         self.params = [p for p in model.parameters() if p.requires_grad]
-        self.flat = None
+        self.buffers = [b for b in model.buffers() if b.dtype.is_floating_point]
+        dev, dt = self.params[0].device, self.params[0].dtype
+        self.numel = sum(p.numel() for p in self.params)
+        self.flat = torch.zeros(self.numel + 1, device=dev, dtype=dt)
+        off = 0
+        for p in self.params:
+            p.grad = self.flat[off:off + p.numel()].view_as(p)
+            off += p.numel()
+        self.timed = timed and dev.type == "cuda"
+        self._events: list = []
+        self.calls = 0
+
+    @property
+    def bucket_bytes(self) -> int:
+        return self.flat.numel() * self.flat.element_size()
+
+    def zero_(self) -> None:
+        self.flat.zero_()
 
     def broadcast_parameters(self, src: int = 0) -> None:
-        if _active():
-            for p in self.params:
-                dist.broadcast(p.data, src)
-
-    def __call__(self, model=None, n_samples: int | None = None) -> None:
+        """rank `src`'s parameters and BatchNorm statistics to every rank, one flat broadcast"""
         if not _active():
             return
-        grads = [p.grad if p.grad is not None else torch.zeros_like(p) for p in self.params]
-        flat = torch._utils._flatten_dense_tensors(grads)
-        if n_samples is None:
-            dist.all_reduce(flat, op=dist.ReduceOp.SUM)
-            flat.div_(dist.get_world_size())
-        else:
-            w = torch.tensor([float(n_samples)], device=flat.device, dtype=flat.dtype)
-            flat.mul_(w)
-            dist.all_reduce(flat, op=dist.ReduceOp.SUM)
-            dist.all_reduce(w, op=dist.ReduceOp.SUM)
-            flat.div_(w.clamp_min(1.0))
-        for p, g in zip(self.params, torch._utils._unflatten_dense_tensors(flat, grads)):
-            p.grad = g.contiguous() if p.grad is None else p.grad.copy_(g)
+        tensors = [p.data for p in self.params] + [b.data for b in self.buffers]
+        flat = torch._utils._flatten_dense_tensors(tensors)
+        dist.broadcast(flat, src)
+        for t, f in zip(tensors, torch._utils._unflatten_dense_tensors(flat, tensors)):
+            t.copy_(f)
+
+    def average_buffers(self) -> None:
+        """BatchNorm running_mean / running_var are updated from each rank's own shard during training; average
+        them so every rank folds the SAME network into its self-play evaluator (one flat all-reduce)."""
+        if not _active() or not self.buffers:
+            return
+        flat = torch._utils._flatten_dense_tensors([b.data for b in self.buffers])
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+        flat.div_(dist.get_world_size())
+        for b, f in zip(self.buffers, torch._utils._unflatten_dense_tensors(flat, self.buffers)):
+            b.data.copy_(f)
+
+    def __call__(self, model=None, n_samples: int | None = None) -> None:
+        """between loss.backward() and optimizer.step() (network.py:93-94)"""
+        if not _active():
+            return
+        for p in self.params:                      # a grad re-created by zero_grad(set_to_none=True) is folded back
+            if p.grad is None or p.grad.data_ptr() < self.flat.data_ptr() or p.grad.data_ptr() >= self.flat.data_ptr() + self.bucket_bytes:
+                self._rebind()
+                break
+        w = 1.0 if n_samples is None else float(n_samples)      # unweighted: every rank counts once
+        if n_samples is not None:
+            self.flat[:-1].mul_(w)
+        self.flat[-1] = w
+        if self.timed:
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+        dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
+        if self.timed:
+            b.record()
+            self._events.append((a, b))
+        self.flat[:-1].div_(self.flat[-1].clamp_min(1.0))
+        self.calls += 1
+
+    def _rebind(self) -> None:
+        off = 0
+        for p in self.params:
+            view = self.flat[off:off + p.numel()].view_as(p)
+            if p.grad is None:
+                view.zero_()
+            elif p.grad.data_ptr() != view.data_ptr():
+                view.copy_(p.grad)
+            p.grad = view
+            off += p.numel()
+
+    def allreduce_ms(self) -> List[float]:
+        """device time of every timed all-reduce so far (synchronises)"""
+        if not self._events:
+            return []
+        self._events[-1][1].synchronize()
+        out = [a.elapsed_time(b) for a, b in self._events]
+        self._events = []
+        return out

@@ -139,6 +139,20 @@ class TreeSearch:
         check(lib().zc_search_results(self._h, _ptr(res), _ptr(visits), _ptr(wsum), _ptr(moves), stride, _stream_ptr(stream)))
         return {"result": res, "visits": visits, "value_sums": wsum, "moves": moves}
 
+    def results_begin(self, stream=None) -> None:
+        """Enqueue the root readout and its device->host copy without waiting (zc_search_results_begin): the next
+        set_roots_dev / run can be enqueued at once.  Collect with results_end()."""
+        check(lib().zc_search_results_begin(self._h, _stream_ptr(stream)))
+        self._begun_n = self.n_trees
+
+    def results_end(self) -> dict:
+        n = getattr(self, "_begun_n", self.n_trees)
+        if getattr(self, "_res_buf", None) is None or len(self._res_buf) < n:
+            self._res_buf = np.zeros(self.max_trees, dtype=ROOT_RESULT_DTYPE)
+        res = self._res_buf[:n]
+        check(lib().zc_search_results_end(self._h, _ptr(res)))
+        return {"result": res, "visits": None, "value_sums": None, "moves": None}
+
     def tree_hash(self, stream=None) -> np.ndarray:
         out = np.zeros(self.n_trees, dtype=np.uint64)
         check(lib().zc_search_tree_hash(self._h, _ptr(out), _stream_ptr(stream)))

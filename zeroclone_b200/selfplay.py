@@ -77,13 +77,23 @@ class DeviceSelfPlay:
         import numpy as np
         torch, _ffi = self.torch, self._ffi
         dev = torch.device("cuda", self.device)
-        n_slots = min(self.n_slots, total_games)
+        if simulations < 1:
+            raise ValueError("DeviceSelfPlay.play: simulations must be >= 1 (a search that never ran has no move to play)")
         item = self.init_rec.dtype.itemsize
         chess = self.game == _ffi.GAME_CHESS
-        with torch.cuda.device(dev):
+        if total_games <= 0:              # a rank whose shard of the games is empty (games_cap < world size)
+            out = {"results": [], "moves": 0, "seconds": 0.0, "games_per_hour": 0.0, "sims_per_sec": 0.0}
+            if record:
+                out["dataset"] = (np.zeros((0,) + tuple(self.backend.TENSOR_SHAPE), dtype=np.float32), np.zeros(0, dtype=np.float32))
+                out["trajectories"] = []
+            return out
+        n_slots = min(self.n_slots, total_games)
+        hist_cap = self.hist_cap
+        with torch.cuda.device(dev), self._mcts.device_lock(self.game, self.device):
             stream = torch.cuda.current_stream().cuda_stream
             states_all = torch.from_numpy(np.repeat(self.init_rec, n_slots).view(np.uint8).reshape(n_slots, item).copy()).to(dev)
-            hist_all = torch.zeros((n_slots, 2, self.hist_cap, 8), dtype=torch.uint8, device=dev) if chess else None
+            hist_all = torch.zeros((n_slots, 2, hist_cap, 8), dtype=torch.uint8, device=dev) if chess else None
+            slot_plies = np.zeros(n_slots, dtype=np.int64)      # plies of the game currently in each slot
             hlen_all = torch.zeros((n_slots, 2), dtype=torch.int32, device=dev) if chess else None
             ts = self._mcts.searcher(self.game, n_slots, simulations, self.device)
             ts.set_policy_freedom(self.pol_freedom)
@@ -107,16 +117,23 @@ class DeviceSelfPlay:
                 res = np.zeros(n, dtype=np.int32)
                 mv = np.zeros(n, dtype=_ffi.CHESS_MOVE_DTYPE)
                 if chess:
+                    if (int(slot_plies[active].max()) + 1) // 2 + 1 >= hist_cap:
+                        # a side's move list is about to fill up: double the history (the reference's deques are
+                        # unbounded, state.h:14); a full history is an error in zc_search_advance, never a silent drop
+                        grown = torch.zeros((n_slots, 2, 2 * hist_cap, 8), dtype=torch.uint8, device=dev)
+                        grown[:, :, :hist_cap] = hist_all
+                        hist_all, hist_cap = grown, 2 * hist_cap
                     hist = hist_all.index_select(0, idx).contiguous()
                     hlen = hlen_all.index_select(0, idx).contiguous()
                     _ffi.check(_ffi.lib().zc_search_advance(ts._h, roots.data_ptr(), ones.data_ptr(), hist.data_ptr(), hlen.data_ptr(),
-                                                           self.hist_cap, res.ctypes.data_as(C.c_void_p), mv.ctypes.data_as(C.c_void_p), stream))
+                                                           hist_cap, res.ctypes.data_as(C.c_void_p), mv.ctypes.data_as(C.c_void_p), stream))
                     hist_all.index_copy_(0, idx, hist)
                     hlen_all.index_copy_(0, idx, hlen)
                 else:
                     _ffi.check(_ffi.lib().zc_search_advance(ts._h, roots.data_ptr(), ones.data_ptr(), None, None, 0,
                                                            res.ctypes.data_as(C.c_void_p), mv.ctypes.data_as(C.c_void_p), stream))
                 plies += n
+                slot_plies[active] += 1
                 new_host = roots.cpu().numpy().view(self.init_rec.dtype).reshape(n) if record else None
                 # bookkeeping per ply, vectorised: which games ended, which slots get the next game (refill
                 # semantics of simulate_games, scripts/train.py:151-170)
@@ -133,6 +150,7 @@ class DeviceSelfPlay:
                     finished += 1
                     if started < total_games:
                         slot_game[slot] = started
+                        slot_plies[slot] = 0
                         started += 1
                         refill.append(int(j))
                     else:

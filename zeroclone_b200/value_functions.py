@@ -74,6 +74,11 @@ class Value:
             self._net = NetEvaluator(self.model, dev)
         return self._net
 
+    def refresh(self) -> None:
+        """self.model was trained further: push its weights into the resident tower (no rebuild, no re-allocation)"""
+        if self._net is not None:
+            self._net.update_weights(self.model.eval())
+
     # ------------------------------------------------------------------ heuristics (host, per state)
     def random_rollout(self, state, args):          # value_functions.py:35-45
         backend = args['backend']
@@ -107,7 +112,14 @@ class Value:
         module.add_safe_globals()
         path = latest if path is None else path
         if os.path.exists(path):
-            self.model = torch.load(path, map_location="cpu", weights_only=False)
+            # the safe loader (no arbitrary unpickling): whole-module pickles of this package's classes, of the
+            # reference's classes (same sub-module names; registered under both paths), or a plain state_dict
+            obj = torch.load(path, map_location="cpu", weights_only=True)
+            if isinstance(obj, dict):
+                self.model = module.ValueNetwork()
+                self.model.load_state_dict(obj)
+            else:
+                self.model = obj
         else:
             self.model = module.ValueNetwork()       # absent checkpoint => random init (value_functions.py:110,125)
         self.model.eval()
