@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define ZC_ABI_VERSION 1
+#define ZC_ABI_VERSION 2
 
 /* error codes */
 #define ZC_OK 0
@@ -150,6 +150,10 @@ int zc_search_run(zc_search *h, int simulations, double c, int batch_size, int e
  * Leaf i of tree t is row t*batch_size+i of `dev_planes` / `dev_values`. */
 int zc_search_begin(zc_search *h, int simulations, double c, int batch_size, int policy, uint64_t seed);
 int zc_search_pending(const zc_search *h); /* simulations per tree still to run */
+/* plane element types of zc_search_select / the tower's operand formats */
+#define ZC_PLANE_BF16 0
+#define ZC_PLANE_F32 1
+#define ZC_PLANE_F16 2
 /* dev_planes: [n_trees*batch_size][C][H][W] (C4: 2x6x7, c4_backend.py:52-61; chess: 17x8x8,
  * chess_backend.cpp:461-521), plane_dtype 0 = bf16, 1 = f32, 2 = f16.  Rows of batches shorter
  * than batch_size (the last batch) are zero-filled. */
@@ -267,14 +271,21 @@ int zc_search_set_policy_freedom(zc_search *h, double policy_freedom);
  *            Connect Four, 17 for chess), then 2*n_blocks convolutions with Cin = 128
  *   conv_b : float32 [1 + 2*n_blocks][128]
  *   head_w : float32 [128], head_b : Linear bias
- * zc_tower_forward evaluates n_leaves positions packed as bf16 planes [n][Cin][H][W] (the layout
- * zc_search_select writes with ZC_PLANE_BF16) into dev_values[n] float32, on `stream`, without
- * synchronising.  Arithmetic: bf16 operands, fp32 accumulation, bf16 activations between layers. */
+ *   plane_dtype : operand format of the tensor-core path, ZC_PLANE_F16 or ZC_PLANE_BF16 (same rate).
+ *            fp16 is what the reference itself evaluates in on a GPU (value_functions.py:6) and is the default of
+ *            the Python host: with 11 significand bits the per-leaf error vs fp32 is ~5e-5 and root values of an
+ *            800-simulation search agree with the fp32 reference within 1e-3 on chess as well as Connect Four;
+ *            bf16 (8 bits, ~5e-4 per leaf) holds 1e-3 at the root on Connect Four only (tests/test_gpu_parity_bench_sets.py).
+ *            Activations saturate at +-65504 instead of overflowing.
+ * zc_tower_forward evaluates n_leaves positions packed as 16-bit planes [n][Cin][H][W] in the tower's format (the
+ * layout zc_search_select writes with the same plane_dtype) into dev_values[n] float32, on `stream`, without
+ * synchronising.  Arithmetic: 16-bit operands, fp32 accumulation, 16-bit activations between layers. */
 typedef struct zc_tower zc_tower;
-int zc_tower_create(int game, int device, int n_blocks, const float *conv_w, const float *conv_b, const float *head_w,
-                    float head_b, zc_tower **out);
+int zc_tower_create(int game, int device, int n_blocks, int plane_dtype, const float *conv_w, const float *conv_b,
+                    const float *head_w, float head_b, zc_tower **out);
 void zc_tower_destroy(zc_tower *t);
-int zc_tower_forward(zc_tower *t, const void *dev_planes_bf16, int n_leaves, float *dev_values, void *stream);
+int zc_tower_forward(zc_tower *t, const void *dev_planes, int n_leaves, float *dev_values, void *stream);
+int zc_tower_plane_dtype(const zc_tower *t);
 /* New weights into an existing tower (same arguments as zc_tower_create): what the training loop does after
  * every cycle (scripts/train.py:143-146 saves latest.pth and the next self-play evaluates with it).  The weight
  * image is re-packed on the host and uploaded on `stream`, ordered after the forwards already enqueued there. */

@@ -32,7 +32,7 @@ def test_every_declared_symbol_is_exported(L):
 
 
 def test_abi_version_and_struct_sizes(L):
-    assert L.zc_abi_version() == 1
+    assert L.zc_abi_version() == 2
     assert C.sizeof(_ffi.C4State) == 24 and C.sizeof(_ffi.ChessState) == 72 and C.sizeof(_ffi.RootResult) == 48
 
 
@@ -63,10 +63,14 @@ def test_tower_refuses_without_gpu_and_checks_arguments(L):
     hw = np.zeros(128, dtype=np.float32)
     h = C.c_void_p()
     args = (w.ctypes.data_as(C.c_void_p), b.ctypes.data_as(C.c_void_p), hw.ctypes.data_as(C.c_void_p), C.c_float(0.0), C.byref(h))
-    assert L.zc_tower_create(7, 0, 8, *args) == _ffi.ZC_EINVAL            # unknown game
-    assert L.zc_tower_create(_ffi.GAME_C4, 0, 9, *args) == _ffi.ZC_EINVAL   # deeper than the reference tower
+    f16 = _ffi.PLANE_F16
+    assert L.zc_tower_create(7, 0, 8, f16, *args) == _ffi.ZC_EINVAL            # unknown game
+    assert L.zc_tower_create(_ffi.GAME_C4, 0, 9, f16, *args) == _ffi.ZC_EINVAL   # deeper than the reference tower
+    assert L.zc_tower_create(_ffi.GAME_C4, 0, 8, _ffi.PLANE_F32, *args) == _ffi.ZC_EINVAL   # tensor-core operands are 16-bit
+    assert L.zc_tower_update_weights(None, *args[:4], None) == _ffi.ZC_EINVAL
+    assert L.zc_tower_fault(None) == 0
     if L.zc_device_count() > 0:
         pytest.skip("a GPU is present")
-    assert L.zc_tower_create(_ffi.GAME_C4, 0, 8, *args) == _ffi.ZC_ENODEVICE
+    assert L.zc_tower_create(_ffi.GAME_C4, 0, 8, f16, *args) == _ffi.ZC_ENODEVICE
     assert b"no CPU path" in L.zc_last_error()
     assert L.zc_tower_forward(None, None, 4, None, None) == _ffi.ZC_EINVAL

@@ -91,9 +91,9 @@ def test_network_leaf_values_and_root_values_within_tolerance():
     planes = torch.from_numpy(np.concatenate(seen)[:4096])
     with torch.no_grad():
         ref = model(planes).view(-1)
-    got = ev(planes.to("cuda", torch.bfloat16)).cpu()
+    got = ev(planes.to("cuda", ev.dtype)).cpu()
     leaf_err = (got - ref).abs().max().item()
-    assert leaf_err < TOL, f"per-leaf |bf16 - fp32| max {leaf_err}"
+    assert leaf_err < TOL, f"per-leaf |{ev.dtype} - fp32| max {leaf_err}"
 
     ts = TreeSearch(_ffi.GAME_C4, n, sims)
     ts.set_roots(roots_array(packed))

@@ -38,29 +38,37 @@ def random_planes(n, shape, seed):
     return x
 
 
+# operand formats of the fused kernel and the per-leaf bound each must hold against fp32: bf16 (8 significand bits)
+# the north-star 1e-3; fp16 (11 bits, the default and the reference's own GPU dtype) five times tighter
+DTYPES = [(torch.float16, 2e-4), (torch.bfloat16, TOL)]
+
+
 @pytest.mark.parametrize("game", ["c4", "chess"])
 @pytest.mark.parametrize("perturb_bn", [False, True])
-def test_tower_matches_fp32_reference(game, perturb_bn):
+@pytest.mark.parametrize("dtype,tol", DTYPES)
+def test_tower_matches_fp32_reference(game, perturb_bn, dtype, tol):
     model, shape = make_model(game, perturb_bn)
     n = 3000
     x = random_planes(n, shape, 1)
     with torch.no_grad():
         ref = model(x).view(-1)
-    ev = NetEvaluator(model, "cuda")
-    got = ev(x.to("cuda", torch.bfloat16)).cpu()
+    ev = NetEvaluator(model, "cuda", dtype)
+    got = ev(x.to("cuda", dtype)).cpu()
     err = (got - ref).abs().max().item()
-    assert err < TOL, f"|fused bf16 - fp32| max {err}"
+    print(f"{game} perturb_bn={perturb_bn} {dtype}: per-leaf |fused - fp32| max {err:.2e}")
+    assert err < tol, f"|fused {dtype} - fp32| max {err}"
     assert ev.launches == 1
 
 
 @pytest.mark.parametrize("game", ["c4", "chess"])
-def test_tower_ragged_batches_and_determinism(game):
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+def test_tower_ragged_batches_and_determinism(game, dtype):
     """every leaf is evaluated independently of its neighbours in the tile and of the batch size:
     the same position must give the same bits at any offset, for any n (incl. n not a multiple of the
     boards per tile, n smaller than one tile, n = 0)"""
     model, shape = make_model(game, True, seed=3)
-    x = random_planes(1500, shape, 2).to("cuda", torch.bfloat16)
-    ev = NetEvaluator(model, "cuda")
+    x = random_planes(1500, shape, 2).to("cuda", dtype)
+    ev = NetEvaluator(model, "cuda", dtype)
     full = ev(x).cpu()
     again = ev(x).cpu()
     assert torch.equal(full, again), "not deterministic"
@@ -78,12 +86,13 @@ def test_tower_ragged_batches_and_determinism(game):
 
 
 @pytest.mark.parametrize("game", ["c4", "chess"])
-def test_tower_agrees_with_torch_bf16_path(game):
+@pytest.mark.parametrize("dtype,tol", DTYPES)
+def test_tower_agrees_with_torch_16bit_path(game, dtype, tol):
     model, shape = make_model(game, False)
-    x = random_planes(2048, shape, 5).to("cuda", torch.bfloat16)
-    a = NetEvaluator(model, "cuda")(x).cpu()
-    b = TorchTowerEvaluator(model, "cuda", torch.bfloat16)(x).cpu()
-    assert (a - b).abs().max().item() < 2 * TOL
+    x = random_planes(2048, shape, 5).to("cuda", dtype)
+    a = NetEvaluator(model, "cuda", dtype)(x).cpu()
+    b = TorchTowerEvaluator(model, "cuda", dtype)(x).cpu()
+    assert (a - b).abs().max().item() < 2 * tol
 
 
 def test_tower_full_batch_size():
@@ -92,7 +101,7 @@ def test_tower_full_batch_size():
     n = 131072
     x = random_planes(n, shape, 7)
     ev = NetEvaluator(model, "cuda")
-    got = ev(x.to("cuda", torch.bfloat16)).cpu()
+    got = ev(x.to("cuda", ev.dtype)).cpu()
     idx = torch.randint(0, n, (2048,), generator=torch.Generator().manual_seed(0))
     idx[-1] = n - 1
     with torch.no_grad():
@@ -101,7 +110,7 @@ def test_tower_full_batch_size():
     assert torch.isfinite(got).all()
     # the CTA-pair / two-tiles-in-flight pipeline must not depend on timing: bit-identical reruns, and the
     # same bits as evaluating a slice on its own (different CTA, tile slot and pair rank for every leaf)
-    xd = x.to("cuda", torch.bfloat16)
+    xd = x.to("cuda", ev.dtype)
     for _ in range(3):
         assert torch.equal(ev(xd).cpu(), got)
     assert torch.equal(ev(xd[70001:70001 + 5000].contiguous()).cpu(), got[70001:70001 + 5000])
@@ -113,9 +122,12 @@ def test_tower_rejects_what_it_cannot_compute():
     with pytest.raises(ValueError):
         ev(torch.zeros(4, *shape, device="cuda", dtype=torch.float32))
     with pytest.raises(ValueError):
-        ev(torch.zeros(4, *shape, dtype=torch.bfloat16))
+        ev(torch.zeros(4, *shape, dtype=ev.dtype))                                        # host tensor
     with pytest.raises(ValueError):
-        NetEvaluator(model, "cuda", torch.float16)
+        ev(torch.zeros(4, *shape, device="cuda", dtype=torch.bfloat16))                   # planes in the other 16-bit format
+    with pytest.raises(ValueError):
+        NetEvaluator(model, "cuda", torch.float32)
+    assert ev.dtype == torch.float16 and NetEvaluator(model, "cuda", torch.bfloat16).dtype == torch.bfloat16
 
 
 def test_tower_soak_random_batches_bit_identical():
@@ -125,7 +137,7 @@ def test_tower_soak_random_batches_bit_identical():
     model, shape = make_model("c4", True, seed=9)
     ev = NetEvaluator(model, "cuda")
     n_all = 20000
-    x = random_planes(n_all, shape, 11).to("cuda", torch.bfloat16)
+    x = random_planes(n_all, shape, 11).to("cuda", ev.dtype)
     ref = ev(x).clone()
     g = torch.Generator().manual_seed(1)
     busy = torch.empty(32 << 20, dtype=torch.uint8, device="cuda")
@@ -149,7 +161,7 @@ def test_tower_with_fewer_blocks(blocks):
     x = random_planes(700, (2, 6, 7), 3)
     with torch.no_grad():
         ref = model(x).view(-1)
-    got = NetEvaluator(model, "cuda")(x.to("cuda", torch.bfloat16)).cpu()
+    got = NetEvaluator(model, "cuda")(x.to("cuda", torch.float16)).cpu()
     assert (got - ref).abs().max().item() < TOL
     with pytest.raises(Exception):
         NetEvaluator(ValueNetwork(blocks=9).eval(), "cuda")

@@ -41,5 +41,5 @@ def test_fused_tower_matches_reference_network_outputs():
     from zeroclone_b200.models.chess_value.network import ValueNetwork
     x, want = fixture()
     ev = NetEvaluator(network_fixture.build(ValueNetwork), "cuda")
-    got = ev(x.to("cuda", torch.bfloat16)).cpu().double()
+    got = ev(x.to("cuda", ev.dtype)).cpu().double()
     assert (got - want).abs().max().item() < 1e-3

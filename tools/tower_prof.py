@@ -13,7 +13,7 @@ else:
     shape = (17, 8, 8)
 torch.manual_seed(0)
 model = ValueNetwork().eval()
-xd = (torch.rand(B, *shape) < 0.3).to("cuda", torch.bfloat16).contiguous()
+xd = (torch.rand(B, *shape) < 0.3).to("cuda", torch.float16).contiguous()
 ev = FusedTowerEvaluator(model, "cuda")
 out = torch.empty(B, dtype=torch.float32, device="cuda")
 reps = int(sys.argv[3]) if len(sys.argv) > 3 else 1

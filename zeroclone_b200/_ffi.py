@@ -16,6 +16,7 @@ ZC_OK, ZC_EINVAL, ZC_ENODEVICE, ZC_ECUDA, ZC_ECAPACITY, ZC_ESTATE = 0, -1, -2, -
 MAX_MOVES = 256
 RESULT_ONGOING = 2
 PLANE_BF16, PLANE_F32, PLANE_F16 = 0, 1, 2
+ABI_VERSION = 2
 
 
 class ZcError(RuntimeError):
@@ -108,7 +109,8 @@ def lib() -> C.CDLL:
     L.zc_c4_rules_batch.argtypes = [i32, vp, i32, vp, vp]
     L.zc_search_advance.argtypes = [vp, vp, vp, vp, vp, i32, vp, vp, vp]
     L.zc_states_to_tensor.argtypes = [i32, vp, i32, vp]
-    L.zc_tower_create.argtypes = [i32, i32, i32, vp, vp, vp, C.c_float, C.POINTER(vp)]
+    L.zc_tower_create.argtypes = [i32, i32, i32, i32, vp, vp, vp, C.c_float, C.POINTER(vp)]
+    L.zc_tower_plane_dtype.argtypes = [vp]
     L.zc_tower_destroy.argtypes = [vp]
     L.zc_tower_destroy.restype = None
     L.zc_tower_forward.argtypes = [vp, vp, i32, vp, vp]
@@ -120,7 +122,7 @@ def lib() -> C.CDLL:
     assert C.sizeof(RootResult) == ROOT_RESULT_DTYPE.itemsize == 48, (C.sizeof(RootResult), ROOT_RESULT_DTYPE.itemsize)
     assert C.sizeof(C4State) == C4_STATE_DTYPE.itemsize == 24
     assert C.sizeof(ChessState) == CHESS_STATE_DTYPE.itemsize == 72
-    if L.zc_abi_version() != 1:
+    if L.zc_abi_version() != ABI_VERSION:
         raise ImportError("libzc_b200.so ABI version mismatch; rebuild")
     _lib = L
     return L

@@ -15,7 +15,7 @@
 //   - a horizontal shift wraps into the neighbouring board at x = 0 / W-1.  The three tap columns
 //     (dx = -1, 0, +1) therefore accumulate into three TMEM accumulators and the epilogue adds the
 //     dx = -1 (dx = +1) accumulator only to rows with x != 0 (x != W-1);
-//   - tcgen05.mma kind::f16 (bf16 x bf16 -> fp32), K = 16, issued by one elected thread from warp-uniform
+//   - tcgen05.mma kind::f16 (fp16 x fp16 or bf16 x bf16 -> fp32: template parameter F16), K = 16, issued by one elected thread from warp-uniform
 //     control flow; per layer and tile 9 taps x 8 k-steps.  CTAs run as pairs (cta_group::2, M = 256 over two
 //     SMs): each CTA keeps its own 128-row tile and HALF of every tap's weights (64 of the 128 output
 //     channels), rank 0 issues for both -- the single-CTA form is bound by shared-memory bandwidth;
@@ -32,6 +32,7 @@
 //     (zc_last_error names the wait) instead of hanging the GPU.
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -62,7 +63,7 @@ static_assert(SMEM_ABUF % 16 == 0 && SMEM_WRING % 16 == 0, "descriptor start add
 static_assert(SMEM_TOTAL <= 227 * 1024, "shared memory budget");
 
 struct Params {
-    const __nv_bfloat16* planes;   // [n_leaves][CIN][H][W]
+    const uint16_t* planes;        // [n_leaves][CIN][H][W], 16-bit values in the tower's operand format (bf16 or fp16)
     const uint8_t* wimg2;          // [n_layers][9 taps][2 halves of N][KCHUNKS][64][8]: what each CTA of a pair holds
     const float* bias;             // [n_layers][128] (BatchNorm folded)
     const float* head_w;           // [128]
@@ -168,7 +169,11 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo, uint3
            ((uint64_t)((sbo >> 4) & 0x3FFFu) << 32) | (1ull << 46);
 }
 // instruction descriptor (InstrDescriptor): c = f32, a = b = bf16, both K-major, N = 128
-constexpr uint32_t IDESC2 = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) << 17) | ((256u >> 4) << 24);   // M = 256 over the pair
+// (a/b format field: 0 = fp16, 1 = bf16 -- same tensor-core rate; fp16 carries 3 more mantissa bits)
+template <bool F16>
+struct Idesc2 {
+    static constexpr uint32_t value = (1u << 4) | ((F16 ? 0u : 1u) << 7) | ((F16 ? 0u : 1u) << 10) | ((128u >> 3) << 17) | ((256u >> 4) << 24);   // M = 256 over the pair
+};
 
 // two fp32 lanes per instruction (FADD2 / FMUL2 / FFMA2): the epilogue's arithmetic in half the issue slots
 __device__ __forceinline__ uint64_t f2_pack(uint32_t lo, uint32_t hi) {
@@ -203,6 +208,22 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
 }
 __device__ __forceinline__ float bf16_lo(uint32_t u) { return __uint_as_float(u << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t u) { return __uint_as_float(u & 0xFFFF0000u); }
+// the activation format of the tower: two 16-bit values per register, bf16 or fp16 (F16)
+template <bool F16>
+__device__ __forceinline__ uint32_t act_pack(float lo, float hi) {
+    if constexpr (F16) {
+        uint32_t r;                       // saturating: an activation beyond 65504 stays finite
+        asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+        return r;
+    } else {
+        return pack_bf16(lo, hi);
+    }
+}
+template <bool F16>
+__device__ __forceinline__ float2 act_unpack(uint32_t u) {
+    if constexpr (F16) return __half22float2(*reinterpret_cast<const __half2*>(&u));
+    else return make_float2(bf16_lo(u), bf16_hi(u));
+}
 
 template <int H_, int W_, int NB_, int CIN_>
 struct Geom {
@@ -217,8 +238,9 @@ using GeomC4 = Geom<6, 7, 3, 2>;      // c4_backend.py:52-61
 using GeomChess = Geom<8, 8, 2, 17>;  // chess_backend.cpp:461-521
 
 // ------------------------------------------------------------------------------------ the kernel
-template <class G>
+template <class G, bool F16>
 __global__ void __launch_bounds__(N_THREADS, 1) k_value_tower(const Params p) {
+    constexpr uint32_t IDESC2 = Idesc2<F16>::value;
     extern __shared__ __align__(128) uint8_t smem[];
     const uint32_t sbase = smem_u32(smem);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -385,8 +407,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) k_value_tower(const Params p) {
                         for (int e = 0; e < 8; ++e) {
                             const int ch = chunk * 8 + e;
                             if (ch < G::CIN) {
-                                const unsigned short v = reinterpret_cast<const unsigned short*>(
-                                    p.planes)[((size_t)leaf * G::CIN + ch) * G::HW + y * G::W + x];
+                                const unsigned short v = p.planes[((size_t)leaf * G::CIN + ch) * G::HW + y * G::W + x];
                                 w[e >> 1] |= (uint32_t)v << ((e & 1) * 16);
                             }
                         }
@@ -461,10 +482,11 @@ __global__ void __launch_bounds__(N_THREADS, 1) k_value_tower(const Params p) {
                             const uint32_t xr = xreg[slot][cc * 8 + (i >> 1)];
                             uint64_t v = f2_add(f2_pack(a0[i], a0[i + 1]), side[cc * 8 + (i >> 1)]);
                             v = f2_add(v, f2_pack(__float_as_uint(bv[e]), __float_as_uint(bv[e + 1])));
-                            v = f2_fma(fres2, f2_pack(xr << 16, xr & 0xFFFF0000u), v);
+                            const float2 xf = act_unpack<F16>(xr);
+                            v = f2_fma(fres2, f2_pack(__float_as_uint(xf.x), __float_as_uint(xf.y)), v);
                             float v0, v1;
                             f2_unpack(v, v0, v1);
-                            const uint32_t pk = pack_bf16(fmaxf(v0, 0.f), fmaxf(v1, 0.f));
+                            const uint32_t pk = act_pack<F16>(fmaxf(v0, 0.f), fmaxf(v1, 0.f));
                             o[i >> 1] = pk;
                             xreg[slot][cc * 8 + (i >> 1)] = keep ? pk : xr;
                         }
@@ -482,8 +504,9 @@ __global__ void __launch_bounds__(N_THREADS, 1) k_value_tower(const Params p) {
 #pragma unroll
                     for (int i = 0; i < 32; ++i) {
                         const float2 hw = __ldg(reinterpret_cast<const float2*>(p.head_w + half * 64) + i);
-                        dot = fmaf(bf16_lo(xreg[slot][i]), hw.x, dot);
-                        dot = fmaf(bf16_hi(xreg[slot][i]), hw.y, dot);
+                        const float2 xf = act_unpack<F16>(xreg[slot][i]);
+                        dot = fmaf(xf.x, hw.x, dot);
+                        dot = fmaf(xf.y, hw.y, dot);
                     }
                     float* pt = part + slot * 2 * MROWS;
                     pt[half * MROWS + r] = valid ? dot : 0.f;

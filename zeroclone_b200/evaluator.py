@@ -89,17 +89,21 @@ class TorchTowerEvaluator:
 class FusedTowerEvaluator:
     """The same network as ONE hand-written sm_100a kernel (csrc/tower.cuh, zc_tower_* in
     include/zc_b200.h): activations of a leaf never leave shared memory between the stem and the head.
-    Call: evaluator(planes[B,C,H,W] bf16 contiguous, out=float32[B])."""
+    Call: evaluator(planes[B,C,H,W] contiguous in `self.dtype`, out=float32[B]).
 
-    dtype = torch.bfloat16
+    dtype: torch.float16 (default) or torch.bfloat16 -- the tensor-core operand format, same speed.  fp16 is the
+    reference's own GPU dtype (value_functions.py:6) and the one that meets the north-star tolerance (root values
+    within 1e-3 of the fp32 reference) on chess as well as Connect Four; bf16 meets it on Connect Four only."""
 
-    def __init__(self, model: nn.Module, device="cuda", dtype: torch.dtype = torch.bfloat16):
+    def __init__(self, model: nn.Module, device="cuda", dtype: torch.dtype = torch.float16):
         import ctypes as C
 
         from . import _ffi
 
-        if dtype != torch.bfloat16:
-            raise ValueError("the fused tower computes in bf16 (fp32 accumulation)")
+        if dtype not in (torch.bfloat16, torch.float16):
+            raise ValueError("the fused tower computes in fp16 or bf16 operands (fp32 accumulation)")
+        self.dtype = dtype
+        plane = _ffi.PLANE_F16 if dtype == torch.float16 else _ffi.PLANE_BF16
         model = model.eval()
         self.device = torch.device(device)
         if self.device.type != "cuda":
@@ -113,7 +117,7 @@ class FusedTowerEvaluator:
         self._h = C.c_void_p()
         index = self.device.index if self.device.index is not None else torch.cuda.current_device()
         self._index = index
-        _ffi.check(_ffi.lib().zc_tower_create(game, index, self.n_blocks, conv_w.ctypes.data_as(C.c_void_p),
+        _ffi.check(_ffi.lib().zc_tower_create(game, index, self.n_blocks, plane, conv_w.ctypes.data_as(C.c_void_p),
                                               conv_b.ctypes.data_as(C.c_void_p), head_w.ctypes.data_as(C.c_void_p),
                                               head_b, C.byref(self._h)))
 
@@ -175,8 +179,8 @@ class FusedTowerEvaluator:
 
         from . import _ffi
 
-        if planes.dtype != torch.bfloat16 or not planes.is_contiguous() or planes.device.type != "cuda":
-            raise ValueError("planes must be a contiguous bf16 CUDA tensor [B, C, H, W]")
+        if planes.dtype != self.dtype or not planes.is_contiguous() or planes.device.type != "cuda":
+            raise ValueError(f"planes must be a contiguous {self.dtype} CUDA tensor [B, C, H, W]")
         n = planes.shape[0]
         if out is None:
             out = torch.empty(n, dtype=torch.float32, device=planes.device)
