@@ -6,7 +6,7 @@
 A step = one pass of the hot path over one batch of synthetic roots: `trees` independent searches of `sims`
 simulations each (Engine.play_mcts_parallel's search phase: select, expand, evaluate, backprop, root readout).
 The headline line is BASELINE.json configs[1]: Connect Four, 4096 concurrent trees x 800 sims with the value network
-(random-init weights, fp16 operands / fp32 accumulation), roots = set B.  Per-GPU work is fixed as N grows (weak scaling): every rank owns its own
+(random-init weights, bf16 operands / fp32 accumulation), roots = set B.  Per-GPU work is fixed as N grows (weak scaling): every rank owns its own
 trees; the search needs no collective.
 
 The same invocation also measures the other configurations of BASELINE.json and reports them under "workloads":
@@ -153,7 +153,7 @@ class Ctx:
         if self.world > 1:
             dist.init_process_group("nccl", device_id=self.dev)
         self.hbm_peak, self.tensor_peak, self.peak_src = read_peaks()
-        self.net_dtype = "f16"      # tensor-core operand format of the value tower: "f16" (default of the engine) or "bf16"
+        self.net_dtype = "auto"     # tensor-core operand format of the value tower: the engine's per-game default, "f16" or "bf16"
 
     def barrier(self):
         if self.world > 1:
@@ -201,8 +201,10 @@ def measure_search(cx: Ctx, name: str, trees: int, sims: int, steps: int, warmup
         else:
             from zeroclone_b200.models.connect4_value.network import ValueNetwork
         torch.manual_seed(0)
-        ev = NetEvaluator(ValueNetwork().eval(), cx.dev, torch.bfloat16 if cx.net_dtype == "bf16" else torch.float16)   # fused sm_100a tower kernel (csrc/tower.cuh)
-        plane_code = _ffi.PLANE_BF16 if cx.net_dtype == "bf16" else _ffi.PLANE_F16
+        want = {"bf16": torch.bfloat16, "f16": torch.float16, "auto": None}[cx.net_dtype]
+        ev = NetEvaluator(ValueNetwork().eval(), cx.dev, want)      # fused sm_100a tower kernel (csrc/tower.cuh)
+        net_dtype = "bf16" if ev.dtype == torch.bfloat16 else "f16"
+        plane_code = _ffi.PLANE_BF16 if ev.dtype == torch.bfloat16 else _ffi.PLANE_F16
         flops_leaf = tower_flops_per_leaf(17, 8, 8) if chess else tower_flops_per_leaf(2, 6, 7)
     heur = {"c4_positional": _ffi.EVAL_C4_POSITIONAL, "c4_terminal": _ffi.EVAL_C4_TERMINAL,
             "chess_crude": _ffi.EVAL_CHESS_CRUDE}.get(wl["evaluator"])
@@ -316,12 +318,12 @@ def measure_search(cx: Ctx, name: str, trees: int, sims: int, steps: int, warmup
         roofline = {"bound": "tensor", "achieved": ach, "peak": cx.tensor_peak, "unit": "TFLOP/s", "frac": ach / cx.tensor_peak,
                     "traffic": tw_b * trees * BATCH,
                     "traffic_source": f"ncu --set full capture {tw_src} (dram bytes per leaf x leaves per launch); not re-measured in this run",
-                    "kernel": "k_value_tower (fused tcgen05 residual tower, %s x %s -> fp32), %d launches of %d leaves" % (cx.net_dtype, cx.net_dtype, n_net, trees * BATCH),
+                    "kernel": "k_value_tower (fused tcgen05 residual tower, %s x %s -> fp32), %d launches of %d leaves" % (net_dtype, net_dtype, n_net, trees * BATCH),
                     "avg_launch_ms": net_ms / max(1, n_net), "share_of_step": net_ms / local_ms, "peak_source": cx.peak_src}
     else:
         roofline = dict(roofline_tree, kernel="k_search_fused (%d simulations per launch)" % sims_done, peak_source=cx.peak_src)
     rec = {"value": value, "unit": "sims/s", "ms_per_step": ms / steps, "steps": steps, "scaling": scaling,
-           "dtype": cx.net_dtype if use_net else "f64",
+           "dtype": net_dtype if use_net else "f64",
            "config": workload_config(name, trees, sims, cx.world, scaling),
            "roofline": roofline, "roofline_tree": roofline_tree,
            "e2e": {"value": e2e_value, "unit": "sims/s", "ms_per_step": e2e_ms / steps, "h2d_bytes_per_step": int(roots.nbytes),
@@ -572,8 +574,9 @@ def main():
     ap.add_argument("--train-games", type=int, default=4096, help="self-play games per GPU of the configs[2] record")
     ap.add_argument("--train-steps", type=int, default=200, help="training steps timed in the configs[2] record")
     ap.add_argument("--cpu-budget", type=float, default=15.0)
-    ap.add_argument("--net-dtype", default="f16", choices=["f16", "bf16"],
-                    help="tensor-core operand format of the value tower (same rate; f16 is the engine's default and the reference's GPU dtype)")
+    ap.add_argument("--net-dtype", default="auto", choices=["auto", "f16", "bf16"],
+                    help="tensor-core operand format of the value tower; auto = the engine's default (bf16 Connect Four, fp16 chess: the "
+                         "cheapest format that holds the 1e-3 root-value bar for the game)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -124,10 +124,10 @@ def test_tower_rejects_what_it_cannot_compute():
     with pytest.raises(ValueError):
         ev(torch.zeros(4, *shape, dtype=ev.dtype))                                        # host tensor
     with pytest.raises(ValueError):
-        ev(torch.zeros(4, *shape, device="cuda", dtype=torch.bfloat16))                   # planes in the other 16-bit format
+        ev(torch.zeros(4, *shape, device="cuda", dtype=torch.float16))                    # planes in the other 16-bit format
     with pytest.raises(ValueError):
         NetEvaluator(model, "cuda", torch.float32)
-    assert ev.dtype == torch.float16 and NetEvaluator(model, "cuda", torch.bfloat16).dtype == torch.bfloat16
+    assert ev.dtype == torch.bfloat16 and NetEvaluator(model, "cuda", torch.float16).dtype == torch.float16      # Connect Four default: bf16
 
 
 def test_tower_soak_random_batches_bit_identical():
@@ -161,7 +161,8 @@ def test_tower_with_fewer_blocks(blocks):
     x = random_planes(700, (2, 6, 7), 3)
     with torch.no_grad():
         ref = model(x).view(-1)
-    got = NetEvaluator(model, "cuda")(x.to("cuda", torch.float16)).cpu()
+    ev = NetEvaluator(model, "cuda")
+    got = ev(x.to("cuda", ev.dtype)).cpu()
     assert (got - ref).abs().max().item() < TOL
     with pytest.raises(Exception):
         NetEvaluator(ValueNetwork(blocks=9).eval(), "cuda")

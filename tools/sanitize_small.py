@@ -9,7 +9,7 @@ from zeroclone_b200.workloads import c4_roots_set_b, chess_roots_set_b
 
 torch.manual_seed(0)
 ev = NetEvaluator(ValueNetwork().eval(), "cuda")
-x = (torch.rand(11, 2, 6, 7) < 0.3).to("cuda", torch.float16)
+x = (torch.rand(11, 2, 6, 7) < 0.3).to("cuda", ev.dtype)
 print("tower", ev(x).cpu().tolist()[:3])
 ts = TreeSearch(_ffi.GAME_C4, 32, 64)
 ts.set_roots(c4_roots_set_b(32))

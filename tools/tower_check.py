@@ -25,9 +25,9 @@ x = (torch.rand(B, *shape) < 0.3).float()
 nref = min(B, 4096)
 with torch.no_grad():
     ref = model(x[:nref]).view(-1)
-xd = x.to("cuda", torch.float16).contiguous()
 fused = FusedTowerEvaluator(model, "cuda")
-cud = TorchTowerEvaluator(model, "cuda", torch.float16)
+xd = x.to("cuda", fused.dtype).contiguous()
+cud = TorchTowerEvaluator(model, "cuda", fused.dtype)
 for n in (1, 2, 3, 4, 7, 300, nref):
     got = fused(xd[:n]).cpu()
     torch.cuda.synchronize()

@@ -13,8 +13,8 @@ else:
     shape = (17, 8, 8)
 torch.manual_seed(0)
 model = ValueNetwork().eval()
-xd = (torch.rand(B, *shape) < 0.3).to("cuda", torch.float16).contiguous()
-ev = FusedTowerEvaluator(model, "cuda")
+ev = FusedTowerEvaluator(model, "cuda", {"f16": torch.float16, "bf16": torch.bfloat16}.get(sys.argv[4]) if len(sys.argv) > 4 else None)
+xd = (torch.rand(B, *shape) < 0.3).to("cuda", ev.dtype).contiguous()
 out = torch.empty(B, dtype=torch.float32, device="cuda")
 reps = int(sys.argv[3]) if len(sys.argv) > 3 else 1
 for _ in range(3 if reps == 1 else 20):

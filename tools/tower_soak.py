@@ -19,7 +19,7 @@ else:
 torch.manual_seed(0)
 ev = NetEvaluator(ValueNetwork().eval(), "cuda")
 N = 40000
-x = (torch.rand(N, *shape) < 0.3).to("cuda", torch.float16).contiguous()
+x = (torch.rand(N, *shape) < 0.3).to("cuda", ev.dtype).contiguous()
 ref = ev(x).clone()
 g = torch.Generator().manual_seed(1)
 t0, launches, leaves = time.time(), 0, 0

@@ -13,6 +13,8 @@ struct C4Game {
     ZC_D static int immediate_value_order(const uint4*, const State&, int, int, int, int j, float, uint64_t, int) { return j; }
     static constexpr int SS = 1;            // state slots per node
     static constexpr int FIRST_SLOTS = 9;   // header + state + up to 7 edges: the whole node in one warp load
+    static constexpr int MAX_K = 7;         // moves per node
+    static_assert(MAX_K <= KEYED_PERM_MAX, "Policy.random on the spine path orders a node's moves with keyed_perm");
     static constexpr int PLANE_ELEMS = 84;  // 2 x 6 x 7 (c4_backend.py:52-61)
     static constexpr int MOVE_SCRATCH = 0;
     static constexpr bool kCheapSpine = true;   // play + legal mask are a handful of instructions

@@ -73,7 +73,8 @@ struct ChessGame {
     // Which move the t-th expansion of a node picks is a function of the node (its key seeds the draws), so the
     // warp replays picks 0 .. nexp+m-1 (lane L owns moves L, L+32, ...) and lane j receives the move of
     // expansion nexp + j.  Called by the whole warp.
-    // (out of line: only Policy.immediate_value runs it)
+    // With freedom = +inf every untried move is a candidate: that is Policy.random (policy_functions.py:10-12).
+    // (out of line: only the two randomised policies run it)
     __device__ __noinline__ static int immediate_value_order(const uint4* node, const State& st, int k, int nexp, int m, int j, float freedom,
                                           uint64_t key, int lane) {
         constexpr int Q = (ZC_MAX_MOVES + 31) / 32;
@@ -103,7 +104,7 @@ struct ChessGame {
                 if ((untried >> q & 1u) && (float)val[q] >= threshold) cand |= 1u << q;
             int total;
             const int before = warp_excl_scan(__popc(cand), lane, total);
-            const int r = (int)(rng_mix(key ^ (0x9E3779B97F4A7C15ull * (uint64_t)(t + 1))) % (uint64_t)max(total, 1));
+            const int r = (int)(pick_draw(key, t) % (uint64_t)max(total, 1));
             int pick = -1;
             if (r >= before && r < before + __popc(cand)) {
                 uint32_t c = cand;

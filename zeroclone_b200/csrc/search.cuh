@@ -76,26 +76,26 @@ ZC_HD uint64_t rng_mix(uint64_t z) {
     return z ^ (z >> 31);
 }
 
-// Keyed pseudo-random bijection of [0,k): three multiply/xorshift/add rounds on b = ceil(log2 k)
-// bits (each round is invertible mod 2^b), cycle-walked into range.  Used for Policy.random
-// (policy_functions.py:10-12): expanding moves in the order perm(0), perm(1), ... draws each next
-// move uniformly from the untried ones, which is what random.choice on the untried list does.
+// Keyed uniformly random ordering of [0,k), k <= 16: element j of a Fisher-Yates shuffle whose t-th draw is a
+// pure function of (key, t).  Used for Policy.random (policy_functions.py:10-12) on nodes with few moves (Connect
+// Four: k <= 7): expanding moves in the order perm(0), perm(1), ... draws each next move uniformly from the untried
+// ones, which is what random.choice on the untried list does -- exactly, not approximately: pick t takes the
+// (draw_t mod (k - t))-th of the remaining elements (chi-square tests on first picks and on pairs,
+// tests/test_gpu_parity_bench_sets.py).  The remaining elements live as 4-bit entries of one 64-bit word.
+// Wider nodes (chess) replay the same process warp-cooperatively: ChessGame::immediate_value_order.
+constexpr int KEYED_PERM_MAX = 16;
+ZC_HD uint64_t pick_draw(uint64_t key, int t) { return rng_mix(key ^ (0x9E3779B97F4A7C15ull * (uint64_t)(t + 1))); }
 ZC_HD int keyed_perm(int k, int j, uint64_t key) {
     if (k <= 1) return 0;
-    int b = 1;
-    while ((1 << b) < k) ++b;
-    const uint32_t mask = (1u << b) - 1u;
-    const uint32_t m1 = ((uint32_t)key | 1u), m2 = ((uint32_t)(key >> 20) | 1u), m3 = ((uint32_t)(key >> 40) | 1u);
-    const uint32_t a1 = (uint32_t)(key >> 8), a2 = (uint32_t)(key >> 29), sh = (uint32_t)((b + 1) >> 1);
-    uint32_t x = (uint32_t)j;
-    do {
-        x = (x * m1 + a1) & mask;
-        x ^= x >> sh;
-        x = (x * m2 + a2) & mask;
-        x ^= x >> sh;
-        x = (x * m3) & mask;
-    } while (x >= (uint32_t)k);
-    return (int)x;
+    uint64_t rest = 0xFEDCBA9876543210ull;
+    int pick = 0;
+    for (int t = 0; t <= j; ++t) {
+        const int r = (int)(pick_draw(key, t) % (uint64_t)(k - t));
+        pick = (int)((rest >> (4 * r)) & 0xFull);
+        const uint64_t low = r ? rest & ((1ull << (4 * r)) - 1ull) : 0ull;
+        rest = low | ((rest >> (4 * r + 4)) << (4 * r));          // drop entry r
+    }
+    return pick;
 }
 
 // j-th move to be expanded at a node with k moves (mcts.cpp:65-78).  first / last element of the
@@ -103,7 +103,7 @@ ZC_HD int keyed_perm(int k, int j, uint64_t key) {
 ZC_D int expansion_order(int policy, int k, int j, uint64_t node_key) {
     if (policy == 0) return j;               // ZC_POLICY_FIRST
     if (policy == 1) return k - 1 - j;       // ZC_POLICY_LAST
-    return keyed_perm(k, j, node_key);       // ZC_POLICY_RANDOM
+    return keyed_perm(k, j, node_key);       // ZC_POLICY_RANDOM (games with k <= KEYED_PERM_MAX)
 }
 
 // UCB1, mcts.cpp:41-45, with the operation sequence of the reference build
@@ -388,9 +388,11 @@ ZC_D bool expand_lazy(const SearchParams& p, typename G::Ctx& gx, uint4* __restr
         typename G::State cs = Pst;
         uint32_t cmisc = 0;
         int ei_iv = 0;
-        if (p.policy == 3) ei_iv = G::immediate_value_order(arena + P, Pst, Pk, Pnexp, m, j, p.policy_freedom, nkey, lane);
+        // random / immediate_value: the warp replays the node's pick process (uniform among the untried moves, resp.
+        // among those within policy_freedom of the best untried capture value)
+        if (p.policy >= 2) ei_iv = G::immediate_value_order(arena + P, Pst, Pk, Pnexp, m, j, p.policy == 3 ? p.policy_freedom : CUDART_INF_F, nkey, lane);
         if (act) {
-            ei = p.policy == 3 ? ei_iv : expansion_order(p.policy, Pk, Pnexp + j, nkey);
+            ei = p.policy >= 2 ? ei_iv : expansion_order(p.policy, Pk, Pnexp + j, nkey);
             cs = G::child(Pst, Pmisc, arena + P, Pk, ei, cmisc);
         }
         const int total = m * (1 + G::SS);

@@ -339,6 +339,7 @@ extern "C" int zc_search_create(int game, int device, int max_trees, int max_sim
     if (e == cudaSuccess) e = alloc((void**)&h->hash_dev, sizeof(unsigned long long) * max_trees);
     if (e != cudaSuccess) {
         std::string msg = std::string("cudaMalloc: ") + cudaGetErrorString(e);
+        cudaGetLastError();      // an allocation failure is not sticky, but it would be reported by the next launch check
         zc_search_destroy(h);
         return fail(ZC_ECUDA, msg);
     }
@@ -364,6 +365,7 @@ extern "C" int zc_search_create(int game, int device, int max_trees, int max_sim
     }
     if (e != cudaSuccess) {     // the handle is not handed out: free what it holds
         std::string msg = std::string("zc_search_create: ") + cudaGetErrorString(e);
+        cudaGetLastError();
         zc_search_destroy(h);
         return fail(ZC_ECUDA, msg);
     }
@@ -374,6 +376,7 @@ extern "C" int zc_search_create(int game, int device, int max_trees, int max_sim
         h->bytes += (int64_t)sb;
         cudaError_t se = cudaMalloc((void**)&h->scratch, sb);
         if (se != cudaSuccess) {
+            cudaGetLastError();
             zc_search_destroy(h);
             return fail(ZC_ECUDA, std::string("cudaMalloc(scratch): ") + cudaGetErrorString(se));
         }

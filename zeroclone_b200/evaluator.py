@@ -91,15 +91,22 @@ class FusedTowerEvaluator:
     include/zc_b200.h): activations of a leaf never leave shared memory between the stem and the head.
     Call: evaluator(planes[B,C,H,W] contiguous in `self.dtype`, out=float32[B]).
 
-    dtype: torch.float16 (default) or torch.bfloat16 -- the tensor-core operand format, same speed.  fp16 is the
-    reference's own GPU dtype (value_functions.py:6) and the one that meets the north-star tolerance (root values
-    within 1e-3 of the fp32 reference) on chess as well as Connect Four; bf16 meets it on Connect Four only."""
+    dtype: the tensor-core operand format, torch.bfloat16 or torch.float16 (same MMA rate; measured on a power-capped
+    B200 fp16 runs ~3 % slower: wider multipliers draw more power).  Default (None) is the cheapest format that meets
+    the north-star tolerance -- root values of an 800-simulation search within 1e-3 of the fp32 reference -- for the
+    game: bf16 on Connect Four (worst root of 128: 1.5e-4), fp16 on chess (bf16: 3.3e-3 at the worst root of 32,
+    fp16 passes; fp16 is also what the reference itself evaluates in on a GPU, value_functions.py:6).
+    tests/test_gpu_parity_bench_sets.py holds both measurements."""
 
-    def __init__(self, model: nn.Module, device="cuda", dtype: torch.dtype = torch.float16):
+    DEFAULT_DTYPE = {2: torch.bfloat16, 17: torch.float16}      # by input planes: Connect Four, chess
+
+    def __init__(self, model: nn.Module, device="cuda", dtype: torch.dtype | None = None):
         import ctypes as C
 
         from . import _ffi
 
+        if dtype is None:
+            dtype = self.DEFAULT_DTYPE.get(model.stem[0].in_channels, torch.float16)
         if dtype not in (torch.bfloat16, torch.float16):
             raise ValueError("the fused tower computes in fp16 or bf16 operands (fp32 accumulation)")
         self.dtype = dtype

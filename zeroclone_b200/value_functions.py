@@ -69,9 +69,10 @@ class Value:
             if not torch.cuda.is_available():
                 raise RuntimeError("the neural evaluator runs on the GPU only (no CPU fallback)")
             dtypes = {"fp16": torch.float16, "f16": torch.float16, "float16": torch.float16, "bf16": torch.bfloat16, "bfloat16": torch.bfloat16}
-            dt = dtypes.get(str(self.init_args.get("dtype", "fp16")))
-            if dt is None:
-                raise ValueError("the neural evaluator is the fused sm_100a tower kernel: fp16 (default) or bf16 operands, fp32 accumulation")
+            want = self.init_args.get("dtype")       # None: the evaluator's per-game default (bf16 Connect Four, fp16 chess)
+            dt = None if want is None else dtypes.get(str(want))
+            if want is not None and dt is None:
+                raise ValueError("the neural evaluator is the fused sm_100a tower kernel: fp16 or bf16 operands, fp32 accumulation")
             dev = torch.device("cuda", self.init_args.get("device", torch.cuda.current_device()))
             self._net = NetEvaluator(self.model, dev, dt)
         return self._net
