@@ -127,8 +127,8 @@ struct ChessGame {
     static constexpr bool kLazyMoves = true;    // leaves are stubs; moves are generated when a node is first expanded
     // the move list of ONE position by the whole warp, left contiguous at the start of the warp's staging area
     // (out of line: three call sites, and the generator is the largest piece of code in the kernel)
-    __device__ __noinline__ static int moves_warp(Ctx& gx, const State& s, uint32_t misc, int lane) {
-        return chess::generate_warp(s, (int)(misc & chess::MISC_TURN), gx.moves - lane, 1, lane);
+    __device__ __noinline__ static int moves_warp(Ctx& gx, const State& s, uint32_t misc, int lane, bool any_only = false) {
+        return chess::generate_warp(s, (int)(misc & chess::MISC_TURN), gx.moves - lane, 1, lane, any_only);
     }
     // ... and packed into a node's move slots by the whole warp (8 moves per slot)
     ZC_D static void store_moves_warp(Ctx& gx, uint4* dst, int k, int lane) {
@@ -148,7 +148,7 @@ struct ChessGame {
             todo &= todo - 1;
             const State os = shfl_state(s, owner);
             const uint32_t om = __shfl_sync(FULL_MASK, misc, owner);
-            const int k = moves_warp(gx, os, om, lane);
+            const int k = moves_warp(gx, os, om, lane, true);      // in check: only "any legal move?" is needed
             if (lane == owner && k == 0) v = 1000.0;
         }
         return v;

@@ -134,8 +134,8 @@ ZC_HD uint64_t ray_until_blocker(int d, uint64_t ray, uint64_t occ) {
 // chess_backend.cpp:85-144 -- is the king of `side` on square ksq attacked, given the enemy sets
 // (all subsets of occ)?  Branch-free over the eight rays: the first piece met along a ray attacks iff it
 // is an enemy slider of that ray's kind.
-ZC_HD bool square_attacked(int side, int ksq, uint64_t occ, uint64_t e_pawn, uint64_t e_knight, uint64_t e_diag,
-                           uint64_t e_orth, uint64_t e_king) {
+ZC_HD_CALL bool square_attacked(int side, int ksq, uint64_t occ, uint64_t e_pawn, uint64_t e_knight, uint64_t e_diag,
+                                uint64_t e_orth, uint64_t e_king) {
     const uint64_t k = bit(ksq);
     // pawns: a white king looks one row up (r-1) for 'p', a black king one row down for 'P'
     const uint64_t pawn_from = side == 0 ? (((k >> 9) & ~FILE_H) | ((k >> 7) & ~FILE_A))
@@ -327,7 +327,11 @@ __device__ __noinline__ int generate_cold(const Board& b, int turn, uint16_t* ou
 // king_dirs order; one ascending mask for a knight; the four pawn moves in their fixed order), filters
 // them with the same legality rule as generate(), and an exclusive scan of the per-piece counts places
 // every piece's moves.  All lanes must call it with the same arguments; out[i * stride] receives move i.
-__device__ __forceinline__ int generate_warp(const Board& b, int turn, uint16_t* out, int stride, int lane) {
+//
+// any_only (warp-uniform; the caller knows the side to move is IN CHECK): answer only "is there a legal move?" -- 1 or 0,
+// nothing written to out[].  check_win (chess_backend.cpp:404-412) needs no more than that for a leaf, and in check every
+// move takes the full make-move test, so stopping at the first legal one found by any lane skips most of the work.
+__device__ __forceinline__ int generate_warp(const Board& b, int turn, uint16_t* out, int stride, int lane, bool any_only = false) {
     if (insufficient_material(b)) return 0;
     const Sets s = derive(b, turn);
     if (zc_popc64(s.own) > 32) {                       // more pieces than lanes (only a contrived FEN): one lane does it
@@ -405,13 +409,17 @@ __device__ __forceinline__ int generate_warp(const Board& b, int turn, uint16_t*
         }
     }
     uint64_t bad = 0;
+    bool found = false;
     while (__any_sync(0xFFFFFFFFu, work != 0)) {
         if (work) {
             const int t = zc_ctz64(work);
             work &= work - 1;
             if (!move_keeps_king_safe(s, turn, wfrom, t, wking)) bad |= bit(t);
+            else found = true;
         }
+        if (any_only && __any_sync(0xFFFFFFFFu, found)) return 1;
     }
+    if (any_only) return 0;
     if (spread_king) {                                 // lanes 24..31 report their step to the king's lane
         const uint32_t king_bad = __ballot_sync(0xFFFFFFFFu, lane >= 24 && bad != 0) >> 24;
         if (own_king_lane) {

@@ -5,9 +5,12 @@
 #ifdef __CUDACC__
 #define ZC_HD __host__ __device__ __forceinline__
 #define ZC_D __device__ __forceinline__
+// one out-of-line copy per kernel: bodies that are large and have several call sites (instruction-cache footprint)
+#define ZC_HD_CALL __host__ __device__ __noinline__
 #else
 #define ZC_HD inline
 #define ZC_D inline
+#define ZC_HD_CALL inline
 #endif
 
 ZC_HD int zc_popc64(uint64_t v) {
