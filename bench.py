@@ -166,6 +166,14 @@ class Ctx:
             self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
         return [float(v) for v in t]
 
+    def gather_floats(self, v: float):
+        """v of every rank, in rank order"""
+        if self.world == 1:
+            return [float(v)]
+        out = [self.torch.zeros(1, dtype=self.torch.float64, device=self.dev) for _ in range(self.world)]
+        self.dist.all_gather(out, self.torch.tensor([v], dtype=self.torch.float64, device=self.dev))
+        return [float(t[0]) for t in out]
+
     def sum_over_ranks(self, vals):
         t = self.torch.tensor(list(vals), dtype=self.torch.float64, device=self.dev)
         if self.world > 1:
@@ -285,6 +293,7 @@ def measure_search(cx: Ctx, name: str, trees: int, sims: int, steps: int, warmup
     e1.record()
     cx.barrier()
     e2e_ms = e0.elapsed_time(e1)
+    ms_by_rank = cx.gather_floats(ms / steps)
     ms, e2e_ms = cx.max_over_ranks([ms, e2e_ms])
     total_sims = cx.world * trees * sims * steps
     value = total_sims / (ms * 1e-3)
@@ -322,7 +331,7 @@ def measure_search(cx: Ctx, name: str, trees: int, sims: int, steps: int, warmup
                     "avg_launch_ms": net_ms / max(1, n_net), "share_of_step": net_ms / local_ms, "peak_source": cx.peak_src}
     else:
         roofline = dict(roofline_tree, kernel="k_search_fused (%d simulations per launch)" % sims_done, peak_source=cx.peak_src)
-    rec = {"value": value, "unit": "sims/s", "ms_per_step": ms / steps, "steps": steps, "scaling": scaling,
+    rec = {"value": value, "unit": "sims/s", "ms_per_step": ms / steps, "ms_per_step_by_rank": ms_by_rank, "steps": steps, "scaling": scaling,
            "dtype": net_dtype if use_net else "f64",
            "config": workload_config(name, trees, sims, cx.world, scaling),
            "roofline": roofline, "roofline_tree": roofline_tree,
@@ -351,6 +360,7 @@ def measure_selfplay(cx: Ctx, name: str, games: int, sims: int) -> dict:
         from zeroclone_b200.games.connect4 import c4_backend as backend
     vname = "network_latest" if use_net else wl["evaluator"].replace("chess_crude", "crude_chess_score")
     vkw = {"model_type": "chess_value" if chess else "connect4_value"} if use_net else {}
+    cx.torch.manual_seed(0)          # the same random-init network as the timed search ("weights" in config)
     sp = DeviceSelfPlay(backend, Value(vname, **vkw), Policy("random"), n_slots=games, device=cx.local)
     spo = sp.play(games, sims, C_UCT, seed=cx.rank, record=False)
     gph = cx.sum_over_ranks([spo["games_per_hour"]])[0]
@@ -392,14 +402,33 @@ def measure_selfplay_train(cx: Ctx, games: int, sims: int, max_steps: int) -> di
            "plies": int(cx.sum_over_ranks([sp["moves"]])[0]), "sims_per_sec": cx.sum_over_ranks([sp["moves"]])[0] * sims / sp_s,
            "positions": int(positions), "train_steps": st["steps"], "train_step_ms": cx.max_over_ranks([st["step_ms"]])[0],
            "train_seconds": tr_s, "train_loss": st["loss"], "allreduce_bytes": st["allreduce_bytes"], "collectives_per_step": 1}
-    if "allreduce_ms_median" in st:
-        med = cx.max_over_ranks([st["allreduce_ms_median"]])[0]
+    if cx.world > 1:
         n = cx.world
-        rec.update({"allreduce_ms_median": med, "allreduce_ms_mean": cx.max_over_ranks([st["allreduce_ms"]])[0],
-                    "allreduce_algbw_GBs": st["allreduce_bytes"] / (med * 1e-3) / 1e9,
-                    "allreduce_busbw_GBs": st["allreduce_bytes"] / (med * 1e-3) / 1e9 * 2 * (n - 1) / n,
+        # (a) inside the training step: CUDA events around every all-reduce on every rank.  A rank that reaches the
+        # collective early also waits for the others there, so the collective itself is the per-call MINIMUM over ranks.
+        per_call = cx.torch.tensor(st.get("allreduce_ms_list", [0.0]), dtype=cx.torch.float64, device=cx.dev)
+        cx.dist.all_reduce(per_call, op=cx.dist.ReduceOp.MIN)
+        in_step = float(per_call.median())
+        waited = cx.max_over_ranks([st.get("allreduce_ms_median", 0.0)])[0]
+        # (b) the same 9.46 MB bucket all-reduced back to back with nothing else on the GPU: the wire time
+        bucket = cx.torch.zeros(st["allreduce_bytes"] // 4, dtype=cx.torch.float32, device=cx.dev)
+        for _ in range(5):
+            cx.dist.all_reduce(bucket)
+        cx.barrier()
+        a, b = cx.torch.cuda.Event(enable_timing=True), cx.torch.cuda.Event(enable_timing=True)
+        reps = 50
+        a.record()
+        for _ in range(reps):
+            cx.dist.all_reduce(bucket)
+        b.record()
+        cx.torch.cuda.synchronize()
+        alone = cx.max_over_ranks([a.elapsed_time(b) / reps])[0]
+        gbs = lambda ms: st["allreduce_bytes"] / (ms * 1e-3) / 1e9
+        rec.update({"allreduce_ms_in_step": in_step, "allreduce_ms_in_step_incl_rank_skew": waited, "allreduce_ms_back_to_back": alone,
+                    "allreduce_algbw_GBs": gbs(alone), "allreduce_busbw_GBs": gbs(alone) * 2 * (n - 1) / n,
+                    "allreduce_in_step_algbw_GBs": gbs(in_step) if in_step > 0 else None,
                     "nvlink_GBs_per_direction_nominal": NVLINK_GBS_PER_DIR,
-                    "allreduce_share_of_train_step": med / cx.max_over_ranks([st["step_ms"]])[0]})
+                    "allreduce_share_of_train_step": in_step / cx.max_over_ranks([st["step_ms"]])[0]})
     return rec
 
 

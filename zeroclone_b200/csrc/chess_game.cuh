@@ -7,7 +7,7 @@
 namespace zc {
 
 struct ChessGame {
-    static constexpr int kMinBlocks = 6;   // resident 128-thread blocks per SM the fused search is compiled for
+    static constexpr int kMinBlocks = 8;   // resident 128-thread blocks per SM the fused search is compiled for
     using State = chess::Board;
     static constexpr int SS = 2;             // four bit planes = 32 bytes
     static constexpr int FIRST_SLOTS = 32;   // header + state + first 29 edges in one warp load

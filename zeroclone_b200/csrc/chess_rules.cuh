@@ -69,6 +69,8 @@ ZC_HD int capture_value(int code) {
 __device__ __align__(64) const uint64_t d_rays_t[64][8] = ZC_RAY_TABLE_T;
 __device__ const uint64_t d_knight[64] = ZC_KNIGHT_TABLE;
 __device__ const uint64_t d_king[64] = ZC_KING_TABLE;
+__device__ __align__(32) const uint64_t d_lines[64][4] = ZC_LINE_TABLE;     // diagonal, anti-diagonal, file, rank through a square
+__device__ const uint64_t d_before[64][64] = ZC_BEFORE_TABLE;               // emission-order predecessors (32 KB)
 #endif
 alignas(64) static const uint64_t h_rays_t[64][8] = ZC_RAY_TABLE_T;
 static const uint64_t h_knight[64] = ZC_KNIGHT_TABLE;
@@ -131,6 +133,30 @@ ZC_HD uint64_t ray_until_blocker(int d, uint64_t ray, uint64_t occ) {
     return f ? ray & ~(f - 1) : ray;
 }
 
+#ifdef __CUDACC__
+// Slider attacks along one line through a square as two subtractions ("o - 2s" in both bit orders): with o the occupied
+// squares of the line (without the slider's own square), s the slider's bit,
+//   attacks = ((o - 2s) ^ reverse(reverse(o) - 2 reverse(s))) & line
+// reaches up to and including the first blocker on either side.  One expression per LINE instead of one scan per
+// direction: a queen's reach is four of these (validated against ray walks for every square and line, tools/ and tests).
+struct LineCtx {
+    uint64_t line[4];      // d_lines[sq]
+    uint64_t s2, s2r;      // 2 * bit(sq), 2 * bit(63 - sq)
+};
+__device__ __forceinline__ LineCtx line_ctx(int sq) {
+    LineCtx c;
+    const ulonglong4 v = *reinterpret_cast<const ulonglong4*>(&d_lines[sq][0]);
+    c.line[0] = v.x; c.line[1] = v.y; c.line[2] = v.z; c.line[3] = v.w;
+    c.s2 = 2ull << sq;
+    c.s2r = 2ull << (63 - sq);
+    return c;
+}
+__device__ __forceinline__ uint64_t line_attacks(const LineCtx& c, int l, uint64_t occ) {
+    const uint64_t o = occ & c.line[l];
+    return ((o - c.s2) ^ __brevll(__brevll(o) - c.s2r)) & c.line[l];
+}
+#endif
+
 // chess_backend.cpp:85-144 -- is the king of `side` on square ksq attacked, given the enemy sets
 // (all subsets of occ)?  Branch-free over the eight rays: the first piece met along a ray attacks iff it
 // is an enemy slider of that ray's kind.
@@ -141,6 +167,13 @@ ZC_HD_CALL bool square_attacked(int side, int ksq, uint64_t occ, uint64_t e_pawn
     const uint64_t pawn_from = side == 0 ? (((k >> 9) & ~FILE_H) | ((k >> 7) & ~FILE_A))
                                          : (((k << 7) & ~FILE_H) | ((k << 9) & ~FILE_A));
     uint64_t hit = (pawn_from & e_pawn) | (knight_targets(ksq) & e_knight) | (king_targets(ksq) & e_king);
+#ifdef __CUDA_ARCH__
+    if (e_diag | e_orth) {
+        const LineCtx lc = line_ctx(ksq);
+        if (e_diag) hit |= (line_attacks(lc, 0, occ) | line_attacks(lc, 1, occ)) & e_diag;
+        if (e_orth) hit |= (line_attacks(lc, 2, occ) | line_attacks(lc, 3, occ)) & e_orth;
+    }
+#else
     if (e_diag | e_orth) {
         uint64_t r[8];
         rays_of<0, 8>(ksq, r);
@@ -149,6 +182,7 @@ ZC_HD_CALL bool square_attacked(int side, int ksq, uint64_t occ, uint64_t e_pawn
         for (int d = 0; d < 8; ++d) ray_hit |= first_blocker_in(d, r[d] & occ, d < 4 ? e_diag : e_orth);
         if (ray_hit) return true;
     }
+#endif
     return hit != 0;
 }
 
@@ -321,12 +355,59 @@ ZC_HD int generate(const Board& b, int turn, uint16_t* out, int stride = 1) {
 // out of line: reached only for a contrived position with more than 32 pieces of one colour
 __device__ __noinline__ int generate_cold(const Board& b, int turn, uint16_t* out, int stride) { return generate(b, turn, out, stride); }
 
-// The same list as generate(), produced by a whole warp for ONE position: lane r owns the side to move's
-// r-th piece in square order (the order the reference scans, chess_backend.cpp:203), builds that piece's
-// targets as up to eight ordered segments (one per direction for sliders and the king -- queen_dirs /
-// king_dirs order; one ascending mask for a knight; the four pawn moves in their fixed order), filters
-// them with the same legality rule as generate(), and an exclusive scan of the per-piece counts places
-// every piece's moves.  All lanes must call it with the same arguments; out[i * stride] receives move i.
+// The king of the side to move: is it attacked, and which own pieces are PINNED to it (the first piece met from the king
+// along a line is own and the next one beyond it is an enemy slider of that line's kind)?  Line form of king_danger().
+__device__ __forceinline__ bool king_danger_lines(int side, int ksq, uint64_t occ, uint64_t own, uint64_t e_pawn, uint64_t e_knight,
+                                                  uint64_t e_diag, uint64_t e_orth, uint64_t e_king, uint64_t& pinned) {
+    const uint64_t k = bit(ksq);
+    const uint64_t pawn_from = side == 0 ? (((k >> 9) & ~FILE_H) | ((k >> 7) & ~FILE_A))
+                                         : (((k << 7) & ~FILE_H) | ((k << 9) & ~FILE_A));
+    uint64_t hit = (pawn_from & e_pawn) | (knight_targets(ksq) & e_knight) | (king_targets(ksq) & e_king);
+    uint64_t pins = 0;
+    if (e_diag | e_orth) {
+        const LineCtx lc = line_ctx(ksq);
+        const uint64_t above = ~((k << 1) - 1);              // squares with a higher index than the king: one side of every line
+#pragma unroll 1
+        for (int l = 0; l < 4; ++l) {
+            const uint64_t sliders = l < 2 ? e_diag : e_orth;
+            if (!(lc.line[l] & sliders)) continue;           // no such slider on this line at all
+            const uint64_t att = line_attacks(lc, l, occ);
+            hit |= att & sliders;
+            const uint64_t blockers = att & own;             // own pieces in direct view of the king (at most one per side)
+            if (!blockers) continue;
+            const uint64_t pinners = line_attacks(lc, l, occ ^ blockers) & ~att & sliders;   // seen only through them
+            if (pinners & above) pins |= blockers & above;
+            if (pinners & ~above) pins |= blockers & ~above;
+        }
+    }
+    pinned = pins;
+    return hit != 0;
+}
+
+// index of the n-th (0-based) set bit of a 64-bit word, lowest first; n < popcount(v).  Binary search over popcounts
+// (the __fns intrinsic is a long software sequence).
+__device__ __forceinline__ int nth_set_bit(uint64_t v, int n) {
+    uint32_t w = (uint32_t)v;
+    int base = 0;
+    int c = __popc(w);
+    if (n >= c) { n -= c; w = (uint32_t)(v >> 32); base = 32; }
+#pragma unroll
+    for (int width = 16; width >= 1; width >>= 1) {
+        const uint32_t low = w & ((1u << width) - 1u);
+        c = __popc(low);
+        if (n >= c) { n -= c; w >>= width; base += width; }
+        else w = low;
+    }
+    return base;
+}
+
+// The same list as generate(), produced by a whole warp for ONE position: lane r owns the side to move's r-th piece in
+// square order (the order the reference scans, chess_backend.cpp:203) and holds ALL its targets as one bitboard -- slider
+// reach from four line expressions, leapers from tables, the (up to four) pawn moves by hand.  The targets are filtered
+// with the same legality rule as generate(); an exclusive scan of the per-piece counts places every piece's moves, and a
+// move's position among its piece's moves -- the reference's per-piece direction order, rays outward -- is the number
+// of the piece's targets that precede it: popcount(targets & d_before[sq][t]) (knights: ascending squares; pawns: push,
+// double push, capture left, capture right).  All lanes must call it with the same arguments; out[i * stride] = move i.
 //
 // any_only (warp-uniform; the caller knows the side to move is IN CHECK): answer only "is there a legal move?" -- 1 or 0,
 // nothing written to out[].  check_win (chess_backend.cpp:404-412) needs no more than that for a leaf, and in check every
@@ -334,78 +415,70 @@ __device__ __noinline__ int generate_cold(const Board& b, int turn, uint16_t* ou
 __device__ __forceinline__ int generate_warp(const Board& b, int turn, uint16_t* out, int stride, int lane, bool any_only = false) {
     if (insufficient_material(b)) return 0;
     const Sets s = derive(b, turn);
-    if (zc_popc64(s.own) > 32) {                       // more pieces than lanes (only a contrived FEN): one lane does it
+    const int n_own = zc_popc64(s.own);
+    if (n_own > 32) {                                  // more pieces than lanes (only a contrived FEN): one lane does it
         int n = 0;
         if (lane == 0) n = generate_cold(b, turn, out, stride);
         return __shfl_sync(0xFFFFFFFFu, n, 0);
     }
     const uint64_t empty = ~s.occ;
-    const uint64_t targets_ok = ~s.own & ~s.e_king;
+    const uint64_t targets_ok = ~s.own & ~s.e_king;    // a king is never captured (:240,261,306,331)
     const bool has_king = s.own_king != 0;
-    const int ksq = has_king ? zc_ctz64(s.own_king) : 0;
+    const int ksq = has_king ? zc_ctz64(s.own_king) : 0;   // find_king: the first king in index order (:68-81)
     uint64_t pinned = 0;
-    const bool checked = has_king && king_danger(turn, ksq, s.occ, s.own, s.e_pawn, s.e_knight, s.e_bishop | s.e_queen,
-                                                 s.e_rook | s.e_queen, s.e_king, pinned);
-    uint64_t seg[8];
-#pragma unroll
-    for (int d = 0; d < 8; ++d) seg[d] = 0;
-    uint32_t asc = 0xACu;                              // bit d: segment d is emitted in ascending square order (dirs 2,3,5,7)
-    int sq = 0;
-    bool king_piece = false;
-    const bool mine = lane < zc_popc64(s.own);
+    const bool checked = has_king && king_danger_lines(turn, ksq, s.occ, s.own, s.e_pawn, s.e_knight, s.e_bishop | s.e_queen,
+                                                       s.e_rook | s.e_queen, s.e_king, pinned);
+    uint64_t targets = 0;                              // this lane's piece may move to these squares (before the legality filter)
+    int sq = 0, type = 0;
+    uint32_t pawn_order = 0;                           // 4 x 6 bits: the pawn's targets in emission order (63 = none)
+    const bool mine = lane < n_own;
     if (mine) {
-        const uint32_t lo = (uint32_t)s.own, hi = (uint32_t)(s.own >> 32);   // square of the own piece of rank `lane`
-        const int n_lo = __popc(lo);
-        sq = lane < n_lo ? (int)__fns(lo, 0, lane + 1) : 32 + (int)__fns(hi, 0, lane - n_lo + 1);
-        const int type = piece_at(b, sq) & 7, r = sq >> 3, c = sq & 7;
-        if (type == PAWN) {                            // single push, double push, capture dc=-1, capture dc=+1
+        sq = nth_set_bit(s.own, lane);
+        type = piece_at(b, sq) & 7;
+        if (type == PAWN) {                            // single push, double push, capture dc=-1, capture dc=+1 (:213-252)
+            const int r = sq >> 3, c = sq & 7;
             const int dir = turn == 0 ? -1 : 1, home = turn == 0 ? 6 : 1;
             const int nr = r + dir;
             if (nr >= 0 && nr < 8) {
-                const int one = nr * 8 + c;
-                if (empty >> one & 1) {
-                    seg[0] = bit(one);
-                    const int two = one + dir * 8;
-                    if (r == home && (empty >> two & 1)) seg[1] = bit(two);
-                }
+                const int one = nr * 8 + c, two = one + dir * 8;
                 const uint64_t capturable = s.enemy & ~s.e_king;
-                if (c > 0 && (capturable >> (one - 1) & 1)) seg[2] = bit(one - 1);
-                if (c < 7 && (capturable >> (one + 1) & 1)) seg[3] = bit(one + 1);
+                const bool p1 = (empty >> one & 1) != 0, p2 = p1 && r == home && (empty >> two & 1) != 0;
+                const bool cl = c > 0 && (capturable >> (one - 1) & 1) != 0, cr = c < 7 && (capturable >> (one + 1) & 1) != 0;
+                targets = (p1 ? bit(one) : 0) | (p2 ? bit(two) : 0) | (cl ? bit(one - 1) : 0) | (cr ? bit(one + 1) : 0);
+                pawn_order = (uint32_t)one | ((uint32_t)(two & 63) << 6) | ((uint32_t)((one - 1) & 63) << 12) | ((uint32_t)((one + 1) & 63) << 18);
             }
         } else if (type == KNIGHT) {
-            seg[0] = knight_targets(sq) & targets_ok;
-            asc = 1u;
-        } else if (type != 0) {                        // king, bishop, rook, queen: per direction, outward
-            uint64_t rr[8];
-            rays_of<0, 8>(sq, rr);
-            king_piece = type == KING;
-            const uint64_t reach = king_piece ? king_targets(sq) : ~0ull;
-            const bool diag = type != ROOK, orth = type != BISHOP;
-#pragma unroll
-            for (int d = 0; d < 8; ++d)
-                if (d < 4 ? diag : orth) seg[d] = ray_until_blocker(d, rr[d], s.occ) & targets_ok & reach;
+            targets = knight_targets(sq) & targets_ok;
+        } else if (type == KING) {
+            targets = king_targets(sq) & targets_ok;
+        } else if (type != 0) {                        // bishop, rook, queen
+            const LineCtx lc = line_ctx(sq);
+            if (type != ROOK) targets |= line_attacks(lc, 0, s.occ) | line_attacks(lc, 1, s.occ);
+            if (type != BISHOP) targets |= line_attacks(lc, 2, s.occ) | line_attacks(lc, 3, s.occ);
+            targets &= targets_ok;
         }
     }
     // The reference's make-move test (:345-358), ONE call site fed by a per-lane work list.  The common case --
     // not in check, so only the king's own steps (and a rare pinned piece) need it -- hands the tested king's
-    // eight candidate steps to lanes 24..31, which own no piece when the side has at most 24 of them; in every
+    // candidate steps to lanes 24..31, one each, which own no piece when the side has at most 24 of them; in every
     // other case a lane walks the targets of its own piece.
-    const int n_own = zc_popc64(s.own);
     const bool spread_king = has_king && !checked && n_own <= 24;
-    const bool own_king_lane = mine && king_piece && sq == ksq;
+    const bool own_king_lane = mine && type == KING && sq == ksq;
     uint64_t work = 0;                                 // targets this lane still has to test
     int wfrom = sq;
-    bool wking = king_piece;
+    bool wking = type == KING;
     if (has_king) {
-        if (spread_king && lane >= 24) {
-#ifdef __CUDA_ARCH__
-            work = __ldg(&d_rays_t[ksq][lane - 24]) & king_targets(ksq) & targets_ok;
-#endif
-            wfrom = ksq;
-            wking = true;
-        } else if (mine && !(spread_king && own_king_lane) && (checked || king_piece || (pinned >> sq & 1))) {
-#pragma unroll
-            for (int d = 0; d < 8; ++d) work |= seg[d];
+        if (spread_king) {
+            const uint64_t ktg = king_targets(ksq) & targets_ok;
+            if (lane >= 24) {
+                if (lane - 24 < zc_popc64(ktg)) work = bit(nth_set_bit(ktg, lane - 24));
+                wfrom = ksq;
+                wking = true;
+            } else if (mine && !own_king_lane && (type == KING || (pinned >> sq & 1))) {
+                work = targets;
+            }
+        } else if (mine && (checked || type == KING || (pinned >> sq & 1))) {
+            work = targets;
         }
     }
     uint64_t bad = 0;
@@ -421,20 +494,14 @@ __device__ __forceinline__ int generate_warp(const Board& b, int turn, uint16_t*
     }
     if (any_only) return 0;
     if (spread_king) {                                 // lanes 24..31 report their step to the king's lane
-        const uint32_t king_bad = __ballot_sync(0xFFFFFFFFu, lane >= 24 && bad != 0) >> 24;
-        if (own_king_lane) {
-#pragma unroll
-            for (int d = 0; d < 8; ++d)
-                if (king_bad >> d & 1u) seg[d] = 0;
-        }
+        const bool rep = lane >= 24;
+        const uint32_t bad_lo = __reduce_or_sync(0xFFFFFFFFu, rep ? (uint32_t)bad : 0u);
+        const uint32_t bad_hi = __reduce_or_sync(0xFFFFFFFFu, rep ? (uint32_t)(bad >> 32) : 0u);
+        if (own_king_lane) targets &= ~(((uint64_t)bad_hi << 32) | bad_lo);
+        if (rep) targets = 0;
     }
-    if (mine && !(spread_king && lane >= 24)) {
-#pragma unroll
-        for (int d = 0; d < 8; ++d) seg[d] &= ~bad;    // a piece's segments are disjoint: a target identifies its move
-    }
-    int cnt = 0;
-#pragma unroll
-    for (int d = 0; d < 8; ++d) cnt += zc_popc64(seg[d]);
+    if (mine && !(spread_king && lane >= 24)) targets &= ~bad;
+    const int cnt = zc_popc64(targets);
     int x = cnt;                                       // exclusive scan over lanes = over pieces in square order
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
@@ -442,16 +509,25 @@ __device__ __forceinline__ int generate_warp(const Board& b, int turn, uint16_t*
         if (lane >= d) x += y;
     }
     const int total = __shfl_sync(0xFFFFFFFFu, x, 31);
-    int pos = x - cnt;
+    const int pos = x - cnt;
+    uint64_t tg = targets;
+    while (tg) {                                       // any order: every move knows its own index
+        const int t = zc_ctz64(tg);
+        tg &= tg - 1;
+        int rank;
+        if (type == PAWN) {
+            rank = 0;
 #pragma unroll
-    for (int d = 0; d < 8; ++d) {
-        const bool up = (asc >> d & 1u) != 0;          // outward from the piece: ascending squares, or descending
-        uint64_t tg = up ? seg[d] : __brevll(seg[d]);  // (walked as ascending bits of the reversed word)
-        while (tg) {
-            const int i = zc_ctz64(tg);
-            tg &= tg - 1;
-            out[(size_t)(pos++) * stride] = pack_move(sq, up ? i : 63 - i);
+            for (int q = 0; q < 3; ++q) {              // targets listed before t in the pawn's fixed order
+                const int tq = (int)(pawn_order >> (6 * q)) & 63;
+                if (tq == t) break;
+                rank += (int)(targets >> tq & 1);
+            }
+        } else {
+            const uint64_t before = type == KNIGHT ? bit(t) - 1 : d_before[sq][t];
+            rank = zc_popc64(targets & before);
         }
+        out[(size_t)(pos + rank) * stride] = pack_move(sq, t);
     }
     __syncwarp();
     return total;

@@ -66,6 +66,7 @@ def train_epochs(model: torch.nn.Module, states: np.ndarray, values: np.ndarray,
         ms = sync.allreduce_ms()
         if ms:
             ms_sorted = sorted(ms)
+            out["allreduce_ms_list"] = ms
             out["allreduce_ms"] = sum(ms) / len(ms)
             out["allreduce_ms_median"] = ms_sorted[len(ms) // 2]
             out["allreduce_calls"] = len(ms)
