@@ -56,6 +56,9 @@ WORKLOADS = {
                             desc="BASELINE configs[3]: chess configs/chess_value.yaml, movegen kernel + value-net leaf batching, "
                                  "2048 trees x 800 sims"),
 }
+# the opt-in PUCT selection mode (stored priors, virtual loss; csrc/puct.cuh) on the c4_heuristic workload: a side record only,
+# the reference has no such mode and therefore no baseline for it
+PUCT_SIDE = dict(base="c4_heuristic", sub_steps=20, virtual_loss=1.0, prior_weight=0)
 C_UCT, BATCH = 1.4, 32
 NVLINK_GBS_PER_DIR = 900.0      # NVLink 5 per GPU and direction (nominal), the denominator of the all-reduce figure
 
@@ -182,7 +185,7 @@ class Ctx:
 
 
 def measure_search(cx: Ctx, name: str, trees: int, sims: int, steps: int, warmup: int, scaling: str = "weak",
-                   first_tree_id: int | None = None):
+                   first_tree_id: int | None = None, puct: dict | None = None):
     """Time `steps` searches of `trees` trees x `sims` sims on this rank (all ranks together: world x trees).
     Returns (record, roots) -- the record carries value, e2e, roofline, roofline_tree, clocks, gpu_launches."""
     import numpy as np
@@ -202,6 +205,8 @@ def measure_search(cx: Ctx, name: str, trees: int, sims: int, steps: int, warmup
     roots_host = roots_pinned.numpy().view(roots.dtype).reshape(trees)       # the e2e input: pinned host memory
     roots_dev = roots_pinned.to(cx.dev)
     ts = TreeSearch(_ffi.GAME_CHESS if chess else _ffi.GAME_C4, trees, sims, device=cx.local)
+    if puct is not None:
+        ts.set_mode(_ffi.SELECT_PUCT, puct["virtual_loss"], puct["prior_weight"])
     ev, flops_leaf = None, 0.0
     if use_net:
         if chess:
@@ -330,7 +335,10 @@ def measure_search(cx: Ctx, name: str, trees: int, sims: int, steps: int, warmup
                     "kernel": "k_value_tower (fused tcgen05 residual tower, %s x %s -> fp32), %d launches of %d leaves" % (net_dtype, net_dtype, n_net, trees * BATCH),
                     "avg_launch_ms": net_ms / max(1, n_net), "share_of_step": net_ms / local_ms, "peak_source": cx.peak_src}
     else:
-        roofline = dict(roofline_tree, kernel="k_search_fused (%d simulations per launch)" % sims_done, peak_source=cx.peak_src)
+        roofline = dict(roofline_tree, kernel="%s (%d simulations per launch)" % ("k_search_fused_puct" if puct else "k_search_fused", sims_done),
+                        peak_source=cx.peak_src)
+        if puct:            # no ncu capture of this kernel; its algorithmic bytes are counted like the UCB1 kernel's (one descent per simulation more)
+            roofline["traffic"], roofline["traffic_source"] = None, "not captured"
     rec = {"value": value, "unit": "sims/s", "ms_per_step": ms / steps, "ms_per_step_by_rank": ms_by_rank, "steps": steps, "scaling": scaling,
            "dtype": net_dtype if use_net else "f64",
            "config": workload_config(name, trees, sims, cx.world, scaling),
@@ -466,6 +474,15 @@ def run_ours(args):
                 subs[name] = {"failed": repr(e)}
                 if cx.world > 1:
                     raise               # ranks would desynchronise: fail loudly instead
+        try:
+            w = WORKLOADS[PUCT_SIDE["base"]]
+            r, _ = measure_search(cx, PUCT_SIDE["base"], w["trees"], w["sims"], PUCT_SIDE["sub_steps"], 3, puct=PUCT_SIDE)
+            r["config"]["select"] = "PUCT, stored priors (uniform for Connect Four), virtual loss %.1f; opt-in mode, not in the reference" % PUCT_SIDE["virtual_loss"]
+            subs["c4_heuristic_puct"] = r
+        except Exception as e:      # noqa: BLE001
+            subs["c4_heuristic_puct"] = {"failed": repr(e)}
+            if cx.world > 1:
+                raise
         if cx.world > 1:
             w = WORKLOADS["chess_crude"]
             per = w["trees"] // cx.world

@@ -120,7 +120,7 @@ int zc_c4_get_move_order(uint8_t *table /* [128][8] */);
 
 /* ---- search handle: replaces get_move() for a whole batch of trees ----------------------- */
 
-/* arena_slots_per_tree: 16-byte slots per tree, 0 = default (C4: exact worst case;
+/* arena_slots_per_tree: 16-byte slots per tree, 0 = default (C4: exact worst case, 11 slots per node;
  * chess: (max_sims+1) * 24 -- leaves are 3-slot stubs, about 5 slots per node in practice; an arena that
  * overflows makes zc_search_results return ZC_ECAPACITY).  Memory = max_trees * arena_slots_per_tree * 16 B. */
 int zc_search_create(int game, int device, int max_trees, int max_sims, int64_t arena_slots_per_tree,
@@ -139,6 +139,26 @@ int zc_search_set_roots_dev(zc_search *h, const void *dev_states, int n, void *s
  * `batch_size` (1..32, the reference default is 32), UCB1 constant c.  Asynchronous on stream. */
 int zc_search_run(zc_search *h, int simulations, double c, int batch_size, int evaluator, int policy,
                   uint64_t seed, void *stream);
+
+/* ---- optional selection rule: PUCT with stored priors and virtual loss -----------------------------------------
+ * The reference selects with UCB1 over frozen batches (mcts.cpp:41-63) and that is the default (ZC_SELECT_UCB1, the
+ * bit-exact path).  ZC_SELECT_PUCT is the AlphaZero-style rule BASELINE.json's north star names; the reference has
+ * no counterpart, so its definition is this library's (zeroclone_b200/csrc/puct.cuh) and its checker is
+ * oracle/zc_oracle.c:zo_search_puct (whole-tree hashes must agree):
+ *   a* = argmax_a  Wa/Na + c * P(a) * sqrt(N + 1) / (1 + Na),   lowest index on ties;   on the way down N += 1,
+ *   Na += 1, Wa -= virtual_loss;  one new node per simulation;  a batch of `batch_size` simulations is selected one
+ *   after the other, evaluated together and backed up in order (Wa += virtual_loss; Wa -= result; result = -result).
+ *   Priors P(a) = (1 + prior_weight * move_value(a)) / sum are stored with each node (one float per edge);
+ *   move_value is the capture value the reference attaches to a chess move (chess_backend.cpp:50-64), 0 for Connect
+ *   Four (uniform priors).  zc_search_set_root_priors replaces the roots' priors (policy head, exploration noise).
+ * Call zc_search_set_mode BEFORE zc_search_set_roots*.  In PUCT mode `c` of zc_search_run / zc_search_begin is c_puct,
+ * `policy` is ignored (the rule itself decides which move is expanded next), the rollout evaluator is not available,
+ * and a leaf deeper than 63 plies below the root is ZC_ECAPACITY. */
+#define ZC_SELECT_UCB1 0
+#define ZC_SELECT_PUCT 1
+int zc_search_set_mode(zc_search *h, int select_mode, double virtual_loss, int prior_weight);
+/* host_priors: float[n_trees][stride], row t = the priors of tree t's root moves in backend order */
+int zc_search_set_root_priors(zc_search *h, const float *host_priors, int stride, void *stream);
 
 /* The same loop cut at the evaluator for ZC_EVAL_EXTERNAL (value.batch, mcts.cpp:112-127):
  *   zc_search_begin(...)

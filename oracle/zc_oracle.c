@@ -692,6 +692,120 @@ ZO_API int zo_search(int game, const void *state, int simulations, double c, int
     return 0;
 }
 
+/* ------------------------------------------------------------------------------------ */
+/*  PUCT with stored priors and virtual loss -- NOT in the reference (mcts.cpp:41-63 is   */
+/*  UCB1).  This is the checker of the library's opt-in ZC_SELECT_PUCT mode               */
+/*  (zeroclone_b200/csrc/puct.cuh, include/zc_b200.h): the same definition written         */
+/*  sequentially over heap nodes.  Parity is between this function and the CUDA kernels    */
+/*  only -- there is no reference behaviour to pin it on ("parity unpinned" for this mode).*/
+/* ------------------------------------------------------------------------------------ */
+
+static int move_value_of(const zo_ctx *cx, const zo_node *n, int a) {
+    return cx->game == ZO_GAME_C4 ? 0 : (int)n->ch_moves[a].val;   /* chess_backend.cpp:50-64; c4_backend.py:50 */
+}
+
+/* a* = argmax_a  Wa/Na + c * P(a) * sqrt(N + 1) / (1 + Na), lowest index on ties; every operation rounded on its own */
+static int puct_pick(const zo_ctx *cx, const zo_node *n, double c, int prior_weight, const float *root_priors) {
+    int wsum = 0;
+    for (int a = 0; a < n->n_moves; ++a) wsum += 1 + prior_weight * move_value_of(cx, n, a);
+    const double sqrtN = sqrt((double)(n->N + 1));
+    int best = -1;
+    double best_v = -INFINITY;
+    for (int a = 0; a < n->n_moves; ++a) {
+        const float P = (root_priors && !n->parent) ? root_priors[a] : (float)(1 + prior_weight * move_value_of(cx, n, a)) / (float)wsum;
+        const double q = n->Na[a] ? n->Wa[a] / (double)n->Na[a] : 0.0;
+        double u = c * (double)P;
+        u = u * sqrtN;
+        u = u / (double)(1 + n->Na[a]);
+        const double v = q + u;
+        if (v > best_v) { best_v = v; best = a; }
+    }
+    return best;
+}
+
+ZO_API int zo_search_puct(int game, const void *state, int simulations, double c, int batch_size, int evaluator,
+                          double vloss, int prior_weight, const float *root_priors, zo_batch_eval_fn ext, void *ext_user,
+                          zo_search_result *res) {
+    zo_ctx cx = {game, evaluator, ZO_POLICY_FIRST, ext, ext_user, 0, 0, 0, 0};
+    const int sbytes = game == ZO_GAME_C4 ? (int)sizeof(zo_c4_state) : (int)sizeof(zo_ch_state);
+    if (batch_size < 1) batch_size = 1;
+    zo_node *root = node_new(&cx, state, NULL, -1);
+    zo_node **pending = (zo_node **)malloc(sizeof(zo_node *) * (size_t)batch_size);
+    uint8_t *pstates = (uint8_t *)malloc((size_t)batch_size * (size_t)sbytes);
+    double *vals = (double *)malloc(sizeof(double) * (size_t)batch_size);
+    int np = 0;
+    for (int i = 0; i <= simulations; ++i) {
+        if (i < simulations) {
+            zo_node *n = root;
+            zo_node *leaf = NULL;
+            for (;;) {
+                if (n->n_moves == 0) { leaf = n; cx.reevaluated_leaves++; break; }      /* its own leaf, again */
+                const int a = puct_pick(&cx, n, c, prior_weight, root_priors);
+                n->N += 1;                                                            /* virtual loss */
+                n->Na[a] += 1;
+                n->Wa[a] -= vloss;
+                if (!n->child[a]) {
+                    uint8_t next[ZO_STATE_BYTES] = {0};
+                    if (game == ZO_GAME_C4) zo_c4_play((const zo_c4_state *)n->state, n->c4_moves[a], (zo_c4_state *)next);
+                    else zo_ch_play((const zo_ch_state *)n->state, &n->ch_moves[a], (zo_ch_state *)next);
+                    n->child[a] = node_new(&cx, next, n, a);
+                    n->n_untried--;
+                    leaf = n->child[a];
+                    break;
+                }
+                n = n->child[a];
+            }
+            leaf->N += 1;
+            cx.sum_leaf_depth += leaf->depth;
+            if (leaf->depth > cx.max_leaf_depth) cx.max_leaf_depth = leaf->depth;
+            pending[np++] = leaf;
+        }
+        if (np >= batch_size || (i == simulations && np > 0)) {
+            if (evaluator == ZO_EVAL_EXTERNAL) {
+                for (int k = 0; k < np; ++k) memcpy(pstates + (size_t)k * (size_t)sbytes, pending[k]->state, (size_t)sbytes);
+                ext(pstates, np, sbytes, vals, ext_user);
+            } else {
+                for (int k = 0; k < np; ++k) vals[k] = zo_eval_state(evaluator, pending[k]->state);
+            }
+            for (int k = 0; k < np; ++k) {                                            /* back up in pending order */
+                double result = vals[k];
+                for (zo_node *n = pending[k]; n->parent; n = n->parent) {
+                    zo_node *p = n->parent;
+                    const int a = n->parent_action;
+                    p->Wa[a] += vloss;
+                    p->Wa[a] -= result;
+                    result = -result;
+                }
+            }
+            np = 0;
+        }
+    }
+    memset(res, 0, sizeof *res);
+    res->n_moves = root->n_moves;
+    int best = -1, best_n = -1;
+    for (int i = 0; i < root->n_moves; ++i) {
+        res->Na[i] = root->Na[i];
+        res->Wa[i] = root->Wa[i];
+        if (game == ZO_GAME_C4) { res->moves[i][0] = (uint8_t)root->c4_moves[i]; }
+        else {
+            res->moves[i][0] = root->ch_moves[i].fr; res->moves[i][1] = root->ch_moves[i].fc;
+            res->moves[i][2] = root->ch_moves[i].tr; res->moves[i][3] = root->ch_moves[i].tc;
+            res->move_val[i] = root->ch_moves[i].val;
+        }
+        if (root->child[i] && root->Na[i] > best_n) { best_n = root->Na[i]; best = i; }
+    }
+    res->best = best;
+    res->root_N = root->N;
+    res->nodes_created = cx.nodes_created;
+    res->sum_leaf_depth = cx.sum_leaf_depth;
+    res->max_leaf_depth = cx.max_leaf_depth;
+    res->reevaluated_leaves = cx.reevaluated_leaves;
+    res->tree_hash = hash_tree(root, 0x5A17C10E5EEDull);
+    node_free(root);
+    free(pending); free(pstates); free(vals);
+    return 0;
+}
+
 ZO_API int zo_sizeof_c4_state(void) { return (int)sizeof(zo_c4_state); }
 ZO_API int zo_sizeof_ch_state(void) { return (int)sizeof(zo_ch_state); }
 ZO_API int zo_sizeof_search_result(void) { return (int)sizeof(zo_search_result); }

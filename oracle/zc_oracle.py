@@ -252,3 +252,35 @@ def search(game: int, state, simulations: int, c: float = 1.4, batch_size: int =
     return OracleSearch(n, res.best, [res.Na[i] for i in range(n)], [res.Wa[i] for i in range(n)], moves,
                         res.nodes_created, res.sum_leaf_depth, res.max_leaf_depth, res.reevaluated_leaves,
                         res.tree_hash, res.root_N)
+
+
+def search_puct(game: int, state, simulations: int, c: float = 1.4, batch_size: int = 32, evaluator: int = 0,
+                virtual_loss: float = 1.0, prior_weight: int = 0, root_priors: Optional[Sequence[float]] = None,
+                external: Optional[Callable[[np.ndarray], np.ndarray]] = None) -> OracleSearch:
+    """The checker of the library's opt-in PUCT mode (zo_search_puct; NOT a reference behaviour: mcts.cpp is UCB1)."""
+    res = SearchResult()
+
+    def _cb(ptr, n, sbytes, out, _user):
+        arr = np.ctypeslib.as_array(ptr, shape=(n, sbytes)).copy()
+        vals = np.asarray(external(arr), dtype=np.float64)
+        for i in range(n):
+            out[i] = vals[i]
+
+    cb = BATCH_EVAL(_cb) if external is not None else BATCH_EVAL()
+    pri = None
+    if root_priors is not None:
+        pri = (C.c_float * len(root_priors))(*[float(x) for x in root_priors])
+    L = lib()
+    L.zo_search_puct.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_double, C.c_int, C.c_int, C.c_double, C.c_int, C.c_void_p,
+                                 BATCH_EVAL, C.c_void_p, C.c_void_p]
+    rc = L.zo_search_puct(game, C.byref(state), simulations, c, batch_size, evaluator, virtual_loss, prior_weight, pri, cb, None, C.byref(res))
+    assert rc == 0
+    n = res.n_moves
+    if game == GAME_C4:
+        moves = [(int(res.moves[i][0]), 0) for i in range(n)]
+    else:
+        moves = [((int(res.moves[i][0]), int(res.moves[i][1]), int(res.moves[i][2]), int(res.moves[i][3])),
+                  float(res.move_val[i])) for i in range(n)]
+    return OracleSearch(n, res.best, [res.Na[i] for i in range(n)], [res.Wa[i] for i in range(n)], moves,
+                        res.nodes_created, res.sum_leaf_depth, res.max_leaf_depth, res.reevaluated_leaves,
+                        res.tree_hash, res.root_N)

@@ -118,7 +118,7 @@ def full_training_run(config_name, *, cycles=30, batch_size=256, epochs=4, games
             emit_stats(stage="cycle_start", cycle=cycle + 1, total_cycles=cycles, games_target=hp["games"], sims=hp["simulations"])
         with timer("SELF-PLAY"):          # device-resident: roots stay in HBM between moves, engine.threads games in flight
             sp = DeviceSelfPlay(engine.backend, value, engine.policy, n_slots=engine.threads, device=local if device.type == "cuda" else None,
-                                batch_size=engine.batch_size).play(my_games, hp["simulations"], hp["c_puct"], seed=cycle * 1000003 + rank)
+                                batch_size=engine.batch_size, mode=engine.select_mode).play(my_games, hp["simulations"], hp["c_puct"], seed=cycle * 1000003 + rank)
             if rank == 0:
                 emit_stats(stage="game_done", cycle=cycle + 1, finished=len(sp["results"]), target=my_games)
         games_h = parallel.reduce_sum([sp["games_per_hour"]])[0]

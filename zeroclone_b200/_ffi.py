@@ -16,6 +16,7 @@ ZC_OK, ZC_EINVAL, ZC_ENODEVICE, ZC_ECUDA, ZC_ECAPACITY, ZC_ESTATE = 0, -1, -2, -
 MAX_MOVES = 256
 RESULT_ONGOING = 2
 PLANE_BF16, PLANE_F32, PLANE_F16 = 0, 1, 2
+SELECT_UCB1, SELECT_PUCT = 0, 1
 ABI_VERSION = 2
 
 
@@ -83,6 +84,8 @@ def lib() -> C.CDLL:
     L.zc_search_set_roots_dev.argtypes = [vp, vp, i32, vp]
     L.zc_search_run.argtypes = [vp, i32, dbl, i32, i32, i32, u64, vp]
     L.zc_search_set_policy_freedom.argtypes = [vp, dbl]
+    L.zc_search_set_mode.argtypes = [vp, i32, dbl, i32]
+    L.zc_search_set_root_priors.argtypes = [vp, vp, i32, vp]
     L.zc_search_begin.argtypes = [vp, i32, dbl, i32, i32, u64]
     L.zc_search_pending.argtypes = [vp]
     L.zc_search_select.argtypes = [vp, vp, i32, vp]

@@ -46,6 +46,7 @@ struct C4Game {
     }
     ZC_HD static uint64_t state_key(const State& s, uint32_t) { return s.cur * 0x9E3779B97F4A7C15ull ^ (s.opp + 0xD1B54A32D192ED03ull) * 0xBF58476D1CE4E5B9ull; }
     ZC_HD static int move_slots(int) { return 0; }                    // moves are implied by the legal mask
+    ZC_HD static int move_value(const uint4*, const State&, int, int) { return 0; }   // c4_backend.py:50: every move is (col, 0)
     ZC_HD static void store_moves(Ctx&, uint4*, int) {}
     // state after the ei-th move (backend order) of `parent`
     ZC_HD static State child(const State& parent, uint32_t, const uint4*, int, int ei, uint32_t& cmisc) {

@@ -64,6 +64,10 @@ struct ChessGame {
         const uint16_t* mv = reinterpret_cast<const uint16_t*>(node + 1 + SS + k);
         return mv[i];
     }
+    // the value the reference attaches to move i: what it captures (chess_backend.cpp:50-64)
+    ZC_HD static int move_value(const uint4* node, const State& st, int k, int i) {
+        return chess::capture_value(chess::piece_at(st, chess::move_to(move_at(node, k, i))));
+    }
     ZC_HD static State child(const State& parent, uint32_t pmisc, const uint4* pnode, int pk, int ei, uint32_t& cmisc) {
         const uint16_t m = move_at(pnode, pk, ei);
         return chess::play(parent, pmisc, chess::move_from(m), chess::move_to(m), cmisc);

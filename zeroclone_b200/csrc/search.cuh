@@ -40,6 +40,8 @@ struct SearchParams {
     int evaluator;
     int policy;
     float policy_freedom;    // Policy.immediate_value only
+    int prior_weight;        // PUCT mode (puct.cuh): priors ~ 1 + prior_weight * move value
+    double vloss;            // PUCT mode: virtual loss
     double c;
     uint64_t seed;
     // split-phase leaf packing
@@ -319,10 +321,37 @@ ZC_D bool expand_spine(const SearchParams& p, typename G::Ctx& gx, uint4* __rest
 // whole warp (one piece per lane), only when the search expands below it: the node the descent ends at, and
 // each node the chain steps into.  One or two warp-wide generations per batch instead of one per simulation.
 // ---------------------------------------------------------------------------------------------
+// ---- stored priors (PUCT mode only, puct.cuh): one float per edge after the node's edges / packed moves
+ZC_HD int prior_slots(int k) { return (k + 3) >> 2; }
+// slots of a complete node (header, state, edges, packed moves, and the priors in PUCT mode)
+template <class G>
+ZC_HD int node_slots(int k, bool with_priors) { return 1 + G::SS + k + G::move_slots(k) + (with_priors ? prior_slots(k) : 0); }
+template <class G>
+ZC_HD float* node_priors(uint4* node, int k) { return reinterpret_cast<float*>(node + 1 + G::SS + k + G::move_slots(k)); }
+template <class G>
+ZC_HD const float* node_priors(const uint4* node, int k) { return reinterpret_cast<const float*>(node + 1 + G::SS + k + G::move_slots(k)); }
+// P(a) = w(a) / sum_b w(b), w(a) = 1 + prior_weight * move_value(a): integers, one IEEE division per edge.  Whole warp;
+// the node's state and moves are in place.
+template <class G>
+ZC_D void write_priors(uint4* node, const typename G::State& st, int k, int prior_weight, int lane) {
+    int wsum = 0;
+    for (int base = 0; base < k; base += 32) {
+        const int a = base + lane;
+        int w = a < k ? 1 + prior_weight * G::move_value(node, st, k, a) : 0;
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) w += __shfl_xor_sync(FULL_MASK, w, d);
+        wsum += w;
+    }
+    float* pri = node_priors<G>(node, k);
+    for (int a = lane; a < k; a += 32)
+        pri[a] = __fdiv_rn((float)(1 + prior_weight * G::move_value(node, st, k, a)), (float)wsum);
+    __syncwarp();
+}
+
 // Turn the stub at `node` into a complete node; returns its (possibly new) slot in `node` and its k.
 template <class G>
 __device__ __noinline__ bool materialize(const SearchParams& p, typename G::Ctx& gx, uint4* __restrict__ arena, TreeCtl& ctl, int lane,
-                      uint32_t& node, const typename G::State& st, uint32_t misc, int& k_out) {
+                      uint32_t& node, const typename G::State& st, uint32_t misc, int& k_out, bool with_priors = false) {
     const uint4 sh = arena[node];
     const int k = G::moves_warp(gx, st, misc, lane);
     k_out = k;
@@ -331,7 +360,7 @@ __device__ __noinline__ bool materialize(const SearchParams& p, typename G::Ctx&
         __syncwarp();
         return true;
     }
-    const uint32_t need = (uint32_t)(1 + G::SS + k + G::move_slots(k));
+    const uint32_t need = (uint32_t)node_slots<G>(k, with_priors);
     if ((uint64_t)ctl.top + need > p.arena_slots) { ctl.status = -4; return false; }
     const uint32_t base = ctl.top;
     for (int t = lane; t < k; t += 32) arena[base + 1 + G::SS + t] = make_uint4(0, 0, 0, 0);   // Na = 0, Wa = 0, no child
@@ -342,6 +371,7 @@ __device__ __noinline__ bool materialize(const SearchParams& p, typename G::Ctx&
         arena[sh.z + 1 + G::SS + hdr_parent_edge(sh)].w = base;        // the parent's children[move_idx] follows the node
     }
     __syncwarp();
+    if (with_priors) write_priors<G>(arena + base, st, k, p.prior_weight, lane);
     ctl.top += need;
     node = base;
     return true;

@@ -14,6 +14,7 @@
 #include "c4_game.cuh"
 #include "chess_game.cuh"
 #include "search.cuh"
+#include "puct.cuh"
 
 namespace zc {
 namespace c4 {
@@ -77,6 +78,9 @@ struct zc_search {
     double sp_c = 1.4;
     uint64_t sp_seed = 0;
     double policy_freedom = 0.0;   // Policy.immediate_value
+    // selection rule (zc_search_set_mode): the reference's UCB1, or PUCT with stored priors and virtual loss (puct.cuh)
+    int select_mode = ZC_SELECT_UCB1, prior_weight = 0, fused_grid_puct = 0;
+    double vloss = 1.0;
 };
 
 // ------------------------------------------------------------------------------- C4 move order
@@ -135,7 +139,7 @@ extern "C" int zc_device_count(void) {
 
 // ------------------------------------------------------------------------------- kernels local to the API
 __global__ void k_set_roots_c4(const zc_c4_state* __restrict__ roots, uint4* __restrict__ arena_all, uint64_t arena_slots,
-                               TreeCtl* __restrict__ ctl, Pending* __restrict__ pending, int n) {
+                               TreeCtl* __restrict__ ctl, Pending* __restrict__ pending, int n, int with_priors) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n) return;
     const zc_c4_state r = roots[t];
@@ -147,9 +151,14 @@ __global__ void k_set_roots_c4(const zc_c4_state* __restrict__ roots, uint4* __r
     arena[0] = make_hdr(0, (uint32_t)k, 0, 0, 0, 0, 0);
     C4Game::store_state(arena + 1, s);
     for (int i = 0; i < k; ++i) arena[2 + i] = make_uint4(0, 0, 0, 0);
+    if (with_priors) {                                   // PUCT mode: uniform priors (every Connect Four move has value 0)
+        for (int i = 0; i < prior_slots(k); ++i) arena[2 + k + i] = make_uint4(0, 0, 0, 0);
+        float* pri = node_priors<C4Game>(arena, k);
+        for (int i = 0; i < k; ++i) pri[i] = __fdiv_rn(1.0f, (float)k);
+    }
     TreeCtl c;
     memset(&c, 0, sizeof c);
-    c.top = (uint32_t)(2 + k);
+    c.top = (uint32_t)node_slots<C4Game>(k, with_priors != 0);
     c.nodes = 1;
     c.root_turn = (uint32_t)r.turn;
     c.tree_id = (uint32_t)t;
@@ -201,7 +210,7 @@ __global__ void k_results_c4(const uint4* __restrict__ arena_all, uint64_t arena
 
 __global__ void k_set_roots_chess(const zc_chess_state* __restrict__ roots, uint4* __restrict__ arena_all,
                                   uint64_t arena_slots, TreeCtl* __restrict__ ctl, Pending* __restrict__ pending,
-                                  uint16_t* __restrict__ scratch, int n) {
+                                  uint16_t* __restrict__ scratch, int n, int with_priors, int prior_weight) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n) return;
     const zc_chess_state r = roots[t];
@@ -218,9 +227,16 @@ __global__ void k_set_roots_chess(const zc_chess_state* __restrict__ roots, uint
     ChessGame::store_state(arena + 1, b);
     for (int i = 0; i < k; ++i) arena[3 + i] = make_uint4(0, 0, 0, 0);
     ChessGame::store_moves(gx, arena + 3 + k, k);
+    if (with_priors) {                                   // PUCT mode: P(a) = (1 + prior_weight * capture value) / sum
+        for (int i = 0; i < prior_slots(k); ++i) arena[3 + k + ChessGame::move_slots(k) + i] = make_uint4(0, 0, 0, 0);
+        int wsum = 0;
+        for (int i = 0; i < k; ++i) wsum += 1 + prior_weight * ChessGame::move_value(arena, b, k, i);
+        float* pri = node_priors<ChessGame>(arena, k);
+        for (int i = 0; i < k; ++i) pri[i] = __fdiv_rn((float)(1 + prior_weight * ChessGame::move_value(arena, b, k, i)), (float)wsum);
+    }
     TreeCtl c;
     memset(&c, 0, sizeof c);
-    c.top = (uint32_t)(3 + k + ChessGame::move_slots(k));
+    c.top = (uint32_t)node_slots<ChessGame>(k, with_priors != 0);
     c.nodes = 1;
     c.root_turn = r.turn;
     c.tree_id = (uint32_t)t;
@@ -316,11 +332,12 @@ extern "C" int zc_search_create(int game, int device, int max_trees, int max_sim
     h->max_sims = max_sims;
     // chess: stubs are 3 slots and about one node in thirty becomes a complete node (~37 slots): 4.9 slots per
     // node measured on configs[4]; 24 leaves a factor 5, and an arena that does overflow is reported, not truncated
-    const int per_node = game == ZC_GAME_C4 ? 1 + C4Game::SS + 7 : 24;
+    // (Connect Four: header + state + 7 edges + 2 prior slots, the exact worst case in either selection mode)
+    const int per_node = game == ZC_GAME_C4 ? node_slots<C4Game>(7, true) : 24;
     h->arena_slots = arena_slots_per_tree > 0 ? (uint64_t)arena_slots_per_tree
                                               : (uint64_t)(max_sims + 1) * per_node + (game == ZC_GAME_C4 ? 0 : 320);   // + a maximal chess root
     h->arena_slots = (h->arena_slots + 1) & ~1ull;   // keep every tree's arena 32-byte aligned
-    h->path_cap = (uint32_t)max_sims + 40u;
+    h->path_cap = std::max((uint32_t)max_sims + 40u, PUCT_PATH_CAP);   // PUCT keeps 64 path entries per simulation of a batch
     auto alloc = [&](void** p, size_t bytes) -> cudaError_t {
         h->bytes += (int64_t)bytes;
         return cudaMalloc(p, bytes);
@@ -427,10 +444,10 @@ static int set_roots_common(zc_search* h, const void* dev_states, int n, cudaStr
     }
     if (h->game == ZC_GAME_C4)
         k_set_roots_c4<<<(n + 127) / 128, 128, 0, st>>>((const zc_c4_state*)dev_states, h->arena, h->arena_slots, h->ctl,
-                                                      h->pending, n);
+                                                      h->pending, n, h->select_mode == ZC_SELECT_PUCT);
     else
         k_set_roots_chess<<<(n + 63) / 64, 64, 0, st>>>((const zc_chess_state*)dev_states, h->arena, h->arena_slots, h->ctl,
-                                                      h->pending, h->scratch, n);
+                                                      h->pending, h->scratch, n, h->select_mode == ZC_SELECT_PUCT, h->prior_weight);
     h->launches++;
     CUDA_TRY(cudaGetLastError());
     return ZC_OK;
@@ -473,6 +490,8 @@ static SearchParams make_params(zc_search* h, int sims, double c, int batch, int
     // Connect Four moves all carry value 0 (c4_backend.py:50): immediate_value picks uniformly = random
     p.policy = (policy == ZC_POLICY_IMMEDIATE_VALUE && h->game == ZC_GAME_C4) ? ZC_POLICY_RANDOM : policy;
     p.policy_freedom = (float)h->policy_freedom;
+    p.prior_weight = h->prior_weight;
+    p.vloss = h->vloss;
     p.c = c;
     p.seed = seed;
     p.scratch = h->scratch;
@@ -500,6 +519,20 @@ extern "C" int zc_search_run(zc_search* h, int simulations, double c, int batch_
     SearchParams p = make_params(h, simulations, c, batch_size, evaluator, policy, seed);
     CUDA_TRY(cudaMemsetAsync(h->work_counter, 0, sizeof(unsigned int), st));
     const int blocks_needed = (h->n_trees * 32 + SEARCH_BLOCK - 1) / SEARCH_BLOCK;
+    if (h->select_mode == ZC_SELECT_PUCT) {
+        if (evaluator == ZC_EVAL_C4_ROLLOUT) return fail(ZC_EINVAL, "PUCT mode: the rollout evaluator is not supported");
+        if (!h->fused_grid_puct) {
+            int occ = 0, sms = 0;
+            ZC_DISPATCH(h->game, CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_search_fused_puct<G>, SEARCH_BLOCK, 0)));
+            CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device));
+            h->fused_grid_puct = occ * sms;
+        }
+        const int grid = blocks_needed < h->fused_grid_puct ? blocks_needed : h->fused_grid_puct;
+        ZC_DISPATCH(h->game, k_search_fused_puct<G><<<grid, SEARCH_BLOCK, 0, st>>>(p));
+        h->launches++;
+        CUDA_TRY(cudaGetLastError());
+        return ZC_OK;
+    }
     const int grid = blocks_needed < h->fused_grid ? blocks_needed : h->fused_grid;
     ZC_DISPATCH(h->game, k_search_fused<G><<<grid, SEARCH_BLOCK, 0, st>>>(p));
     h->launches++;
@@ -511,6 +544,51 @@ extern "C" int zc_search_set_policy_freedom(zc_search* h, double policy_freedom)
     if (int rc = check_handle(h)) return rc;
     if (!(policy_freedom >= 0.0)) return fail(ZC_EINVAL, "policy_freedom must be >= 0");
     h->policy_freedom = policy_freedom;
+    return ZC_OK;
+}
+
+// The selection rule of the handle.  Call before zc_search_set_roots*: PUCT roots carry their priors.
+extern "C" int zc_search_set_mode(zc_search* h, int select_mode, double virtual_loss, int prior_weight) {
+    if (int rc = check_handle(h)) return rc;
+    if (select_mode != ZC_SELECT_UCB1 && select_mode != ZC_SELECT_PUCT) return fail(ZC_EINVAL, "unknown selection mode");
+    if (!(virtual_loss >= 0.0) || prior_weight < 0 || prior_weight > 1000) return fail(ZC_EINVAL, "bad virtual_loss or prior_weight");
+    h->select_mode = select_mode;
+    h->vloss = virtual_loss;
+    h->prior_weight = prior_weight;
+    h->n_trees = 0;          // roots have to be set again in the new mode
+    h->sp_left = 0;
+    return ZC_OK;
+}
+
+template <class G>
+__global__ void k_set_root_priors(uint4* __restrict__ arena_all, uint64_t arena_slots, int n, const float* __restrict__ priors, int stride) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    uint4* root = arena_all + (uint64_t)t * arena_slots;
+    const int k = (int)hdr_k(root[0]);
+    float* pri = node_priors<G>(root, k);
+    for (int a = 0; a < k && a < stride; ++a) pri[a] = priors[(size_t)t * stride + a];
+}
+
+extern "C" int zc_search_set_root_priors(zc_search* h, const float* host_priors, int stride, void* stream) {
+    if (int rc = check_handle(h)) return rc;
+    if (h->select_mode != ZC_SELECT_PUCT) return fail(ZC_ESTATE, "set_root_priors: the handle is not in PUCT mode");
+    if (h->n_trees < 1) return fail(ZC_ESTATE, "no roots set");
+    if (!host_priors || stride < 1 || stride > ZC_MAX_MOVES) return fail(ZC_EINVAL, "set_root_priors: bad priors or stride");
+    CUDA_TRY(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    float* dev = nullptr;
+    const size_t bytes = sizeof(float) * (size_t)h->n_trees * stride;
+    CUDA_TRY(cudaMalloc((void**)&dev, bytes));
+    cudaError_t e = cudaMemcpyAsync(dev, host_priors, bytes, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) {
+        ZC_DISPATCH(h->game, k_set_root_priors<G><<<(h->n_trees + 127) / 128, 128, 0, st>>>(h->arena, h->arena_slots, h->n_trees, dev, stride));
+        h->launches++;
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaFree(dev);
+    if (e != cudaSuccess) return fail(ZC_ECUDA, std::string("set_root_priors: ") + cudaGetErrorString(e));
     return ZC_OK;
 }
 
@@ -538,7 +616,8 @@ extern "C" int zc_search_select(zc_search* h, void* dev_planes, int plane_dtype,
     p.planes = dev_planes;
     p.plane_dtype = plane_dtype;
     const int grid = (h->n_trees * 32 + SEARCH_BLOCK - 1) / SEARCH_BLOCK;
-    ZC_DISPATCH(h->game, k_select<G><<<grid, SEARCH_BLOCK, 0, st>>>(p, h->sp_left));
+    if (h->select_mode == ZC_SELECT_PUCT) ZC_DISPATCH(h->game, k_select_puct<G><<<grid, SEARCH_BLOCK, 0, st>>>(p, h->sp_left));
+    else ZC_DISPATCH(h->game, k_select<G><<<grid, SEARCH_BLOCK, 0, st>>>(p, h->sp_left));
     h->launches++;
     CUDA_TRY(cudaGetLastError());
     h->sp_selected = h->sp_left < h->sp_batch ? h->sp_left : h->sp_batch;
@@ -554,7 +633,8 @@ extern "C" int zc_search_backprop(zc_search* h, const float* dev_values, void* s
     SearchParams p = make_params(h, h->sp_left, h->sp_c, h->sp_batch, ZC_EVAL_EXTERNAL, h->sp_policy, h->sp_seed);
     p.values = dev_values;
     const int grid = (h->n_trees * 32 + SEARCH_BLOCK - 1) / SEARCH_BLOCK;
-    ZC_DISPATCH(h->game, k_backprop<G><<<grid, SEARCH_BLOCK, 0, st>>>(p));
+    if (h->select_mode == ZC_SELECT_PUCT) ZC_DISPATCH(h->game, k_backprop_puct<G><<<grid, SEARCH_BLOCK, 0, st>>>(p));
+    else ZC_DISPATCH(h->game, k_backprop<G><<<grid, SEARCH_BLOCK, 0, st>>>(p));
     h->launches++;
     CUDA_TRY(cudaGetLastError());
     h->sp_left -= h->sp_selected;

@@ -48,6 +48,7 @@ class Engine:
             self.values = list(value_functions)
         self.threads = self.config.get("threads", 1)
         self.batch_size = int(self.config.get("mcts", {}).get("batch_size", 32))   # extra key; reference default 32
+        self.select_mode = mcts.select_mode(self.config.get("mcts"))               # extra keys; default = the reference's UCB1
         self.last_search: dict = {}
         # the REST server calls these methods from a thread pool: game bookkeeping and the shared device search
         # handle are used by one request at a time (the reference searched a private tree per request)
@@ -135,7 +136,7 @@ class Engine:
                 continue
             value_fn = self.values[self.states[group[0]].turn]
             out = mcts.search_batch([self.states[i] for i in group], value_fn, self.policy, self.backend,
-                                    int(simulations), float(c), self.batch_size, stats=True)
+                                    int(simulations), float(c), self.batch_size, stats=True, mode=self.select_mode)
             for j, idx in enumerate(group):
                 self.last_search[idx] = {"visits": out["visits"][j][:out["result"][j]["n_moves"]].copy(),
                                          "value_sums": out["value_sums"][j][:out["result"][j]["n_moves"]].copy(),

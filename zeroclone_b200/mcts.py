@@ -88,9 +88,20 @@ def _device_pieces(value, policy, backend):
     return game, value.device_spec(game), policy.device_policy
 
 
+def select_mode(cfg: dict | None) -> tuple:
+    """(select, virtual_loss, prior_weight) from the optional `mcts:` keys `select: ucb1|puct`, `virtual_loss`, `prior_weight`
+    (extra keys; the reference's YAMLs have none of them and get its UCB1)."""
+    cfg = cfg or {}
+    name = str(cfg.get("select", "ucb1")).lower()
+    if name not in ("ucb1", "puct"):
+        raise ValueError(f"mcts.select must be 'ucb1' or 'puct', not {name!r}")
+    return (_ffi.SELECT_PUCT if name == "puct" else _ffi.SELECT_UCB1, float(cfg.get("virtual_loss", 1.0)), int(cfg.get("prior_weight", 0)))
+
+
 def search_batch(states: Sequence, value, policy, backend, simulations: int, c: float, batch_size: int = 32,
-                 seed: int | None = None, stats: bool = False) -> dict:
-    """Search all `states` at once; returns TreeSearch.results() plus 'moves_out' (backend move objects)."""
+                 seed: int | None = None, stats: bool = False, mode: tuple | None = None) -> dict:
+    """Search all `states` at once; returns TreeSearch.results() plus 'moves_out' (backend move objects).
+    mode: select_mode(...) tuple; None = the reference's UCB1."""
     game, (kind, ev), pol = _device_pieces(value, policy, backend)
     n = len(states)
     roots = np.zeros(n, dtype=backend.STATE_DTYPE)
@@ -102,6 +113,7 @@ def search_batch(states: Sequence, value, policy, backend, simulations: int, c: 
         raise ValueError("simulations must be >= 1")
     with device_lock(game):
         ts = searcher(game, n, simulations)
+        ts.set_mode(*(mode or (_ffi.SELECT_UCB1, 1.0, 0)))
         ts.set_roots(roots)
         ts.set_policy_freedom(getattr(policy, "device_freedom", 0.0))
         if kind == "builtin":

@@ -66,6 +66,17 @@ class TreeSearch:
         check(lib().zc_search_set_roots_dev(self._h, C.c_void_p(dev_ptr), n, _stream_ptr(stream)))
         self.n_trees = n
 
+    def set_mode(self, select: int = _ffi.SELECT_UCB1, virtual_loss: float = 1.0, prior_weight: int = 0) -> None:
+        """Selection rule of the following searches: the reference's UCB1 (default, bit-exact) or the opt-in PUCT with stored
+        priors and virtual loss (include/zc_b200.h, csrc/puct.cuh).  Call before set_roots."""
+        check(lib().zc_search_set_mode(self._h, int(select), float(virtual_loss), int(prior_weight)))
+        self.n_trees = 0
+
+    def set_root_priors(self, priors: np.ndarray, stream=None) -> None:
+        """PUCT mode: float32[n_trees, stride] priors of every root's moves (backend order), e.g. from a policy head"""
+        priors = np.ascontiguousarray(priors, dtype=np.float32)
+        check(lib().zc_search_set_root_priors(self._h, _ptr(priors), priors.shape[1], _stream_ptr(stream)))
+
     def set_policy_freedom(self, policy_freedom: float) -> None:
         """`policy_freedom` of Policy.immediate_value (policy_functions.py:16)"""
         check(lib().zc_search_set_policy_freedom(self._h, float(policy_freedom)))

@@ -51,7 +51,7 @@ class DeviceSelfPlay:
     """
 
     def __init__(self, backend, value, policy, n_slots: int, device: int | None = None, batch_size: int = 32,
-                 hist_cap: int = 512):
+                 hist_cap: int = 512, mode: tuple | None = None):
         import torch
 
         from . import _ffi, mcts
@@ -59,6 +59,7 @@ class DeviceSelfPlay:
         self.backend, self.value, self.policy = backend, value, policy
         self.game = backend.ZC_GAME
         self.n_slots, self.batch_size, self.hist_cap = n_slots, batch_size, hist_cap
+        self.mode = mode or (_ffi.SELECT_UCB1, 1.0, 0)        # mcts.select_mode(config["mcts"]); default = the reference's UCB1
         self.device = torch.cuda.current_device() if device is None else device
         self.kind, self.ev = value.device_spec(self.game)
         self.pol = policy.device_policy
@@ -97,6 +98,7 @@ class DeviceSelfPlay:
             hlen_all = torch.zeros((n_slots, 2), dtype=torch.int32, device=dev) if chess else None
             ts = self._mcts.searcher(self.game, n_slots, simulations, self.device)
             ts.set_policy_freedom(self.pol_freedom)
+            ts.set_mode(*self.mode)
             slot_game = list(range(n_slots))              # game id played in each slot
             started, finished = n_slots, 0
             results = [None] * total_games
