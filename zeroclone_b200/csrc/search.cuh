@@ -87,12 +87,18 @@ ZC_HD uint64_t rng_mix(uint64_t z) {
 // Wider nodes (chess) replay the same process warp-cooperatively: ChessGame::immediate_value_order.
 constexpr int KEYED_PERM_MAX = 16;
 ZC_HD uint64_t pick_draw(uint64_t key, int t) { return rng_mix(key ^ (0x9E3779B97F4A7C15ull * (uint64_t)(t + 1))); }
-ZC_HD int keyed_perm(int k, int j, uint64_t key) {
+// (out of line: only Policy.random runs it, and inlined it costs the deterministic policies registers)
+#ifdef __CUDACC__
+__host__ __device__ __noinline__
+#else
+inline
+#endif
+int keyed_perm(int k, int j, uint64_t key) {
     if (k <= 1) return 0;
     uint64_t rest = 0xFEDCBA9876543210ull;
     int pick = 0;
     for (int t = 0; t <= j; ++t) {
-        const int r = (int)(pick_draw(key, t) % (uint64_t)(k - t));
+        const int r = (int)((uint32_t)(pick_draw(key, t) >> 32) % (uint32_t)(k - t));
         pick = (int)((rest >> (4 * r)) & 0xFull);
         const uint64_t low = r ? rest & ((1ull << (4 * r)) - 1ull) : 0ull;
         rest = low | ((rest >> (4 * r + 4)) << (4 * r));          // drop entry r

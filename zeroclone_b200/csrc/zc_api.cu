@@ -380,6 +380,9 @@ extern "C" int zc_search_create(int game, int device, int max_trees, int max_sim
         e = cudaEventCreateWithFlags(&h->ev_copy_done[i], cudaEventDisableTiming);
         if (e == cudaSuccess) e = alloc((void**)&h->res_dev2[i], sizeof(zc_root_result) * max_trees);
     }
+    // struct padding of zc_root_result is never written by the readout kernels: give it a defined value once
+    if (e == cudaSuccess) e = cudaMemset(h->res_dev, 0, sizeof(zc_root_result) * max_trees);
+    for (int i = 0; i < 2 && e == cudaSuccess; ++i) e = cudaMemset(h->res_dev2[i], 0, sizeof(zc_root_result) * max_trees);
     if (e != cudaSuccess) {     // the handle is not handed out: free what it holds
         std::string msg = std::string("zc_search_create: ") + cudaGetErrorString(e);
         cudaGetLastError();
