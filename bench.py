@@ -65,8 +65,8 @@ NVLINK_GBS_PER_DIR = 900.0      # NVLink 5 per GPU and direction (nominal), the 
 # dram__bytes_read.sum + dram__bytes_write.sum from `ncu --set full` captures kept under profiles/ (NOT re-measured in this
 # run: a profiler cannot run inside the timed region).  Tower: per evaluated leaf; tree kernels: per simulation.
 NCU_TRAFFIC = {
-    "tower": {"connect4": (204.9, "profiles/r1d_k_value_tower_c4_ncu.txt"), "chess": (2325.1, "profiles/r1d_k_value_tower_chess_ncu.txt")},
-    "tree": {"connect4": (148.0, "profiles/r1b_k_search_fused_c4_ncu.txt"), "chess": (80.0, "profiles/r1d_k_search_fused_chess_ncu.txt")},
+    "tower": {"connect4": (205.4, "profiles/r2_k_value_tower_c4_ncu.txt"), "chess": (2337.7, "profiles/r2_k_value_tower_chess_ncu.txt")},
+    "tree": {"connect4": (152.4, "profiles/r2_k_search_fused_c4_ncu.txt"), "chess": (273.5, "profiles/r2_k_search_fused_chess_ncu.txt")},
 }
 
 
