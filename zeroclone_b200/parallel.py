@@ -146,6 +146,23 @@ class GradSync:
         self.flat[:-1].div_(self.flat[-1].clamp_min(1.0))
         self.calls += 1
 
+    def reduce_bucket(self) -> None:
+        """The collective alone, for a caller that fills the bucket itself (training.py's CUDA-graph step): gradients already
+        weighted by the sample count, the count in the last element; the caller divides afterwards."""
+        if not _active():
+            return
+        if self.timed:
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+        dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
+        if self.timed:
+            b.record()
+            self._events.append((a, b))
+        self.calls += 1
+
+    def rebind(self) -> None:
+        self._rebind()
+
     def _rebind(self) -> None:
         off = 0
         for p in self.params:
