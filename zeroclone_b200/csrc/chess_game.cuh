@@ -70,7 +70,7 @@ struct ChessGame {
     }
     ZC_HD static State child(const State& parent, uint32_t pmisc, const uint4* pnode, int pk, int ei, uint32_t& cmisc) {
         const uint16_t m = move_at(pnode, pk, ei);
-        return chess::play(parent, pmisc, chess::move_from(m), chess::move_to(m), cmisc);
+        return chess::play_generated(parent, pmisc, chess::move_from(m), chess::move_to(m), cmisc);   // the node's own generated move
     }
     // Policy.immediate_value (policy_functions.py:14-17) as mcts.cpp:65-78 applies it: every expansion of a node
     // picks uniformly among its untried moves whose capture value move[1] is >= (best untried value - freedom).

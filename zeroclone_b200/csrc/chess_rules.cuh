@@ -556,6 +556,26 @@ ZC_HD Board play(const Board& b, uint32_t misc, int from, int to, uint32_t& misc
     misc_out = m;
     return n;
 }
+// The same for a move the generator produced.  Generated king moves are single steps (castling is never generated,
+// :322-340), so the rook hop of :388-391 cannot trigger and the move is: lift the piece's four code bits off `from`, drop
+// them on `to` (replacing what stood there), promote a pawn that reaches the last row (:396-397: pawn 001 -> queen 101).
+ZC_HD Board play_generated(const Board& b, uint32_t misc, int from, int to, uint32_t& misc_out) {
+    const uint64_t f = bit(from), t = bit(to), keep = ~(f | t);
+    const int pc = piece_at(b, from), fc = from & 7, tr = to >> 3;
+    uint32_t m = misc ^ MISC_TURN;
+    if (pc == KING || (pc == ROOK && fc == 7)) m &= ~MISC_WCK;               // :382-385 (any row, as written)
+    if (pc == KING || (pc == ROOK && fc == 0)) m &= ~MISC_WCQ;
+    if (pc == (KING | 8) || (pc == (ROOK | 8) && fc == 7)) m &= ~MISC_BCK;
+    if (pc == (KING | 8) || (pc == (ROOK | 8) && fc == 0)) m &= ~MISC_BCQ;
+    Board n;
+    n.p0 = (b.p0 & keep) | ((pc & 1) ? t : 0);
+    n.p1 = (b.p1 & keep) | ((pc & 2) ? t : 0);
+    n.p2 = (b.p2 & keep) | ((pc & 4) ? t : 0);
+    n.p3 = (b.p3 & keep) | ((pc & 8) ? t : 0);
+    if ((tr == 0 && pc == PAWN) || (tr == 7 && pc == (PAWN | 8))) n.p2 |= t;
+    misc_out = m;
+    return n;
+}
 // does this move reset the fifty-ply counter?  (:380: pawn move or any capture)
 ZC_HD bool resets_fifty(const Board& b, int from, int to) {
     return (piece_at(b, from) & 7) == PAWN || piece_at(b, to) != 0;
