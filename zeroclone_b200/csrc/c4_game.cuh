@@ -62,28 +62,34 @@ struct C4Game {
     }
     ZC_HD static double eval_child(const State& s, uint32_t m, int, int evaluator, uint64_t key) { return eval(s, m, evaluator, key); }
 
-    // leaf -> network input row: plane 0 = side to move, plane 1 = opponent, [r][c] with r = 0 the top row
-    ZC_D static void pack_planes(void* planes, int dtype, size_t row, bool valid, bool in_range, const State& s, uint32_t) {
-        if (!in_range) return;
+    // leaves -> network input rows, by the whole warp: plane 0 = side to move, plane 1 = opponent, [r][c] with r = 0 the
+    // top row (c4_backend.py:52-61).  Lane i holds leaf i (row row0 + i); rows are written one after the other with lane q
+    // storing the row's q-th group of four cells, so every store instruction covers one contiguous run of the batch.
+    ZC_D static void pack_planes(void* planes, int dtype, size_t row0, int n_valid, int n_rows, const State& s, uint32_t, int lane) {
+        constexpr int GROUPS = PLANE_ELEMS / 4;                 // 21 groups of four cells per row
         const uint32_t one16 = dtype == 2 ? 0x3C00u : 0x3F80u;   // f16 : bf16
-#pragma unroll 1
-        for (int q = 0; q < 21; ++q) {
-            uint32_t bits = 0;
+        for (int i = 0; i < n_rows; ++i) {
+            const State ls = shfl_state(s, i);
+            if (lane < GROUPS) {
+                uint32_t bits = 0;
+                if (i < n_valid) {
 #pragma unroll
-            for (int t = 0; t < 4; ++t) {
-                const int idx = q * 4 + t, pl = idx / 42, cell = idx % 42, r = cell / 7, c = cell % 7;
-                const uint64_t bb = pl == 0 ? s.cur : s.opp;
-                bits |= (uint32_t)((bb >> (c * 7 + (5 - r))) & 1ull) << t;
-            }
-            if (!valid) bits = 0;
-            if (dtype == 1) {
-                float4 f = make_float4(bits & 1 ? 1.f : 0.f, bits & 2 ? 1.f : 0.f, bits & 4 ? 1.f : 0.f, bits & 8 ? 1.f : 0.f);
-                reinterpret_cast<float4*>(planes)[row * 21 + q] = f;
-            } else {
-                uint2 h;
-                h.x = (bits & 1 ? one16 : 0u) | (bits & 2 ? one16 << 16 : 0u);
-                h.y = (bits & 4 ? one16 : 0u) | (bits & 8 ? one16 << 16 : 0u);
-                reinterpret_cast<uint2*>(planes)[row * 21 + q] = h;
+                    for (int t = 0; t < 4; ++t) {
+                        const int idx = lane * 4 + t, pl = idx / 42, cell = idx % 42, r = cell / 7, c = cell % 7;
+                        const uint64_t bb = pl == 0 ? ls.cur : ls.opp;
+                        bits |= (uint32_t)((bb >> (c * 7 + (5 - r))) & 1ull) << t;
+                    }
+                }
+                const size_t o = (row0 + (size_t)i) * GROUPS + (size_t)lane;
+                if (dtype == 1) {
+                    reinterpret_cast<float4*>(planes)[o] =
+                        make_float4(bits & 1 ? 1.f : 0.f, bits & 2 ? 1.f : 0.f, bits & 4 ? 1.f : 0.f, bits & 8 ? 1.f : 0.f);
+                } else {
+                    uint2 h;
+                    h.x = (bits & 1 ? one16 : 0u) | (bits & 2 ? one16 << 16 : 0u);
+                    h.y = (bits & 4 ? one16 : 0u) | (bits & 8 ? one16 << 16 : 0u);
+                    reinterpret_cast<uint2*>(planes)[o] = h;
+                }
             }
         }
     }

@@ -184,16 +184,21 @@ struct ChessGame {
         const bool on = pl == 12 ? !(misc & chess::MISC_TURN) : (misc >> (pl - 12)) & 1u;
         return on ? ~0ull : 0ull;
     }
-    ZC_D static void pack_planes(void* planes, int dtype, size_t row, bool valid, bool in_range, const State& s, uint32_t misc) {
-        if (!in_range) return;
+    // By the whole warp: lane i holds leaf i (row row0 + i); rows are written one after the other, lane q storing groups
+    // q, q + 32, ... of four cells (17 planes x 16 groups per row), so every store instruction covers a contiguous run.
+    ZC_D static void pack_planes(void* planes, int dtype, size_t row0, int n_valid, int n_rows, const State& s, uint32_t misc, int lane) {
+        constexpr int GROUPS = PLANE_ELEMS / 4;                 // 272
         const uint32_t one16 = dtype == 2 ? 0x3C00u : 0x3F80u;
+        for (int i = 0; i < n_rows; ++i) {
+            const State ls = shfl_state(s, i);
+            const uint32_t lm = __shfl_sync(FULL_MASK, misc, i);
+            const bool valid = i < n_valid;
 #pragma unroll 1
-        for (int pl = 0; pl < 17; ++pl) {
-            const uint64_t bb = valid ? plane_bits(s, misc, pl) : 0ull;
-#pragma unroll 1
-            for (int q = 0; q < 16; ++q) {
+            for (int g = lane; g < GROUPS; g += 32) {
+                const int pl = g >> 4, q = g & 15;
+                const uint64_t bb = valid ? plane_bits(ls, lm, pl) : 0ull;
                 const uint32_t bits = (uint32_t)(bb >> (4 * q)) & 0xFu;
-                const size_t o = (row * 17 + pl) * 16 + q;
+                const size_t o = (row0 + (size_t)i) * GROUPS + (size_t)g;
                 if (dtype == 1) {
                     reinterpret_cast<float4*>(planes)[o] =
                         make_float4(bits & 1 ? 1.f : 0.f, bits & 2 ? 1.f : 0.f, bits & 4 ? 1.f : 0.f, bits & 8 ? 1.f : 0.f);

@@ -252,7 +252,7 @@ __global__ void __launch_bounds__(SEARCH_BLOCK) k_select_puct(SearchParams p, in
         p.ctl[tree] = ctl;
     }
     pd->info[lane] = ok ? info : 0u;
-    G::pack_planes(p.planes, p.plane_dtype, (size_t)tree * (size_t)p.batch_size + (size_t)lane, ok && lane < B, lane < p.batch_size, st, misc);
+    G::pack_planes(p.planes, p.plane_dtype, (size_t)tree * (size_t)p.batch_size, ok ? B : 0, p.batch_size, st, misc, lane);
 }
 
 template <class G>

@@ -682,8 +682,7 @@ __global__ void __launch_bounds__(SEARCH_BLOCK) k_select(SearchParams p, int sim
         p.ctl[tree] = ctl;
     }
     pd->info[lane] = ok ? leaf.info : 0u;
-    G::pack_planes(p.planes, p.plane_dtype, (size_t)tree * (size_t)p.batch_size + (size_t)lane,
-                   ok && lane < B, lane < p.batch_size, leaf.st, leaf.misc);
+    G::pack_planes(p.planes, p.plane_dtype, (size_t)tree * (size_t)p.batch_size, ok ? B : 0, p.batch_size, leaf.st, leaf.misc, lane);
 }
 
 // Split phase 2: backprop the batch with the caller's values.
