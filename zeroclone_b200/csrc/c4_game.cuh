@@ -19,7 +19,8 @@ struct C4Game {
     static constexpr int MOVE_SCRATCH = 0;
     static constexpr bool kCheapSpine = true;   // play + legal mask are a handful of instructions
     struct Ctx {};
-    ZC_D static Ctx make_ctx(const SearchParams&, unsigned, int) { return Ctx(); }
+    static constexpr int WARP_MOVES = 8;    // no staging list: moves are implied by the legal mask
+    ZC_D static Ctx make_ctx(const SearchParams&, unsigned, int, uint16_t*) { return Ctx(); }
 
     ZC_D static State state_from_lanes(const uint4& v) {
         const uint4 s = shfl4(v, 1);

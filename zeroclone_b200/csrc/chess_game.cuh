@@ -15,14 +15,17 @@ struct ChessGame {
     static constexpr bool kCheapSpine = false;  // a chain node needs a full move generation: expand level by level
     static constexpr int MOVE_SCRATCH = chess::MAX_PSEUDO;   // pseudo-legal staging (>= 218 legal), multiple of 8
 
+    static constexpr int WARP_MOVES = chess::MAX_PSEUDO;   // entries of the per-warp staging list in shared memory
     struct Ctx {
-        uint16_t* moves;   // this lane's move list: entry i at moves[i * stride]
+        uint16_t* moves;   // this lane's move list (serial generator, cold paths): entry i at moves[i * stride], global memory
         int stride;        // 32 in the search: the lanes of a warp interleave their lists, lane-parallel accesses coalesce
+        uint16_t* wmoves;  // the warp generator's list for ONE position: contiguous, in shared memory
     };
-    ZC_D static Ctx make_ctx(const SearchParams& p, unsigned warp_slot, int lane) {
+    ZC_D static Ctx make_ctx(const SearchParams& p, unsigned warp_slot, int lane, uint16_t* warp_moves) {
         Ctx c;
         c.moves = p.scratch + (size_t)warp_slot * 32 * MOVE_SCRATCH + (size_t)lane;
         c.stride = 32;
+        c.wmoves = warp_moves;
         return c;
     }
     ZC_D static State state_from_lanes(const uint4& v) {
@@ -129,14 +132,14 @@ struct ChessGame {
         return chess::generate(s, (int)(misc & chess::MISC_TURN), mv);
     }
     static constexpr bool kLazyMoves = true;    // leaves are stubs; moves are generated when a node is first expanded
-    // the move list of ONE position by the whole warp, left contiguous at the start of the warp's staging area
+    // the move list of ONE position by the whole warp, left contiguous in the warp's shared-memory staging list
     // (out of line: three call sites, and the generator is the largest piece of code in the kernel)
     __device__ __noinline__ static int moves_warp(Ctx& gx, const State& s, uint32_t misc, int lane, bool any_only = false) {
-        return chess::generate_warp(s, (int)(misc & chess::MISC_TURN), gx.moves - lane, 1, lane, any_only);
+        return chess::generate_warp(s, (int)(misc & chess::MISC_TURN), gx.wmoves, 1, lane, any_only);
     }
     // ... and packed into a node's move slots by the whole warp (8 moves per slot)
     ZC_D static void store_moves_warp(Ctx& gx, uint4* dst, int k, int lane) {
-        const uint4* src = reinterpret_cast<const uint4*>(gx.moves - lane);
+        const uint4* src = reinterpret_cast<const uint4*>(gx.wmoves);
         for (int i = lane; i < move_slots(k); i += 32) dst[i] = src[i];
     }
     // crude_chess_score of freshly created children (value_functions.py:49-55), one child per active lane, without

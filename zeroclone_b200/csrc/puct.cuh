@@ -206,6 +206,7 @@ ZC_D void puct_backup_batch(const SearchParams& p, uint4* __restrict__ arena, co
 // ---- kernels: the same three shapes as search.cuh
 template <class G, int MINB = G::kMinBlocks>
 __global__ void __launch_bounds__(SEARCH_BLOCK, MINB) k_search_fused_puct(SearchParams p) {
+    __shared__ __align__(16) uint16_t warp_moves[SEARCH_BLOCK / 32][G::WARP_MOVES];   // chess: the warp generator's move list
     const int lane = threadIdx.x & 31;
     for (;;) {
         int tree = 0;
@@ -215,7 +216,7 @@ __global__ void __launch_bounds__(SEARCH_BLOCK, MINB) k_search_fused_puct(Search
         uint4* arena = p.arena + (uint64_t)tree * p.arena_slots;
         uint2* path = p.path + (uint64_t)tree * p.path_cap;
         TreeCtl ctl = p.ctl[tree];
-        typename G::Ctx gx = G::make_ctx(p, (blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5, lane);
+        typename G::Ctx gx = G::make_ctx(p, (blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5, lane, warp_moves[threadIdx.x >> 5]);
         for (int done = 0; done < p.simulations && ctl.status == 0;) {
             const int B = min(p.batch_size, p.simulations - done);
             uint32_t info, misc;
@@ -232,6 +233,7 @@ __global__ void __launch_bounds__(SEARCH_BLOCK, MINB) k_search_fused_puct(Search
 
 template <class G>
 __global__ void __launch_bounds__(SEARCH_BLOCK) k_select_puct(SearchParams p, int sims_left) {
+    __shared__ __align__(16) uint16_t warp_moves[SEARCH_BLOCK / 32][G::WARP_MOVES];   // chess: the warp generator's move list
     const int lane = threadIdx.x & 31;
     const int tree = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
     if (tree >= p.n_trees) return;
@@ -244,7 +246,7 @@ __global__ void __launch_bounds__(SEARCH_BLOCK) k_select_puct(SearchParams p, in
     typename G::State st = typename G::State();
     double value = 0.0;
     bool ok = B > 0;
-    typename G::Ctx gx = G::make_ctx(p, (unsigned)tree, lane);
+    typename G::Ctx gx = G::make_ctx(p, (unsigned)tree, lane, warp_moves[threadIdx.x >> 5]);
     if (ok) ok = puct_select_batch<G, false>(p, gx, arena, path, ctl, B, lane, info, st, misc, value);
     if (lane == 0) {
         pd->B = ok ? B : 0;

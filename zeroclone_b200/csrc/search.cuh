@@ -632,6 +632,7 @@ constexpr int SEARCH_BLOCK = 128;
 // (mcts.cpp:129-149) for every tree.  Warps pull tree indices from a global counter.
 template <class G, int MINB = G::kMinBlocks>
 __global__ void __launch_bounds__(SEARCH_BLOCK, MINB) k_search_fused(SearchParams p) {
+    __shared__ __align__(16) uint16_t warp_moves[SEARCH_BLOCK / 32][G::WARP_MOVES];   // chess: the warp generator's move list
     __shared__ WarpPlan plans[SEARCH_BLOCK / 32];
     WarpPlan& wp = plans[threadIdx.x >> 5];
     const int lane = threadIdx.x & 31;
@@ -643,7 +644,7 @@ __global__ void __launch_bounds__(SEARCH_BLOCK, MINB) k_search_fused(SearchParam
         uint4* arena = p.arena + (uint64_t)tree * p.arena_slots;
         uint2* path = p.path + (uint64_t)tree * p.path_cap;
         TreeCtl ctl = p.ctl[tree];
-        typename G::Ctx gx = G::make_ctx(p, (blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5, lane);
+        typename G::Ctx gx = G::make_ctx(p, (blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5, lane, warp_moves[threadIdx.x >> 5]);
         for (int done = 0; done < p.simulations && ctl.status == 0;) {
             const int B = min(p.batch_size, p.simulations - done);
             int d0, D;
@@ -660,6 +661,7 @@ __global__ void __launch_bounds__(SEARCH_BLOCK, MINB) k_search_fused(SearchParam
 // Split phase 1 (external evaluator): select+expand one batch per tree, pack leaf planes.
 template <class G>
 __global__ void __launch_bounds__(SEARCH_BLOCK) k_select(SearchParams p, int sims_left) {
+    __shared__ __align__(16) uint16_t warp_moves[SEARCH_BLOCK / 32][G::WARP_MOVES];   // chess: the warp generator's move list
     __shared__ WarpPlan plans[SEARCH_BLOCK / 32];
     WarpPlan& wp = plans[threadIdx.x >> 5];
     const int lane = threadIdx.x & 31;
@@ -674,7 +676,7 @@ __global__ void __launch_bounds__(SEARCH_BLOCK) k_select(SearchParams p, int sim
     Leaf<G> leaf;
     leaf.info = 0;
     bool ok = B > 0;
-    typename G::Ctx gx = G::make_ctx(p, (unsigned)tree, lane);
+    typename G::Ctx gx = G::make_ctx(p, (unsigned)tree, lane, warp_moves[threadIdx.x >> 5]);
     if (ok) ok = select_expand<G, false>(p, gx, arena, path, ctl, B, lane, wp, d0, D, leaf);
     if (lane == 0) {
         pd->B = ok ? B : 0;

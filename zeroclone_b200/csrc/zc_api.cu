@@ -221,6 +221,7 @@ __global__ void k_set_roots_chess(const zc_chess_state* __restrict__ roots, uint
     ChessGame::Ctx gx;
     gx.moves = scratch + (size_t)t * 32 * ChessGame::MOVE_SCRATCH;
     gx.stride = 1;
+    gx.wmoves = nullptr;      // the warp generator is not used here
     const int k = ChessGame::count_moves(gx, b, misc);
     uint4* arena = arena_all + (uint64_t)t * arena_slots;
     arena[0] = make_hdr(0, (uint32_t)k, 0, 0, 0, misc, 0);
