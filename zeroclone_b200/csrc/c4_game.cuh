@@ -21,6 +21,7 @@ struct C4Game {
     struct Ctx {};
     static constexpr int WARP_MOVES = 8;    // no staging list: moves are implied by the legal mask
     ZC_D static Ctx make_ctx(const SearchParams&, unsigned, int, uint16_t*) { return Ctx(); }
+    ZC_D static int random_order(Ctx&, int, int, int, int j, uint64_t, int) { return j; }   // never reached: Connect Four orders with keyed_perm
 
     ZC_D static State state_from_lanes(const uint4& v) {
         const uint4 s = shfl4(v, 1);

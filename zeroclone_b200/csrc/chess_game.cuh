@@ -75,13 +75,50 @@ struct ChessGame {
         const uint16_t m = move_at(pnode, pk, ei);
         return chess::play_generated(parent, pmisc, chess::move_from(m), chess::move_to(m), cmisc);   // the node's own generated move
     }
+    // Policy.random (policy_functions.py:10-12) as mcts.cpp:65-78 applies it: every expansion draws uniformly from the node's
+    // untried moves, i.e. the node's moves are expanded in a uniformly random order.  That order is fixed per node by giving
+    // move i the key hash(node key, i) and expanding in ascending key order (ties by index) -- a uniformly random
+    // permutation, the same distribution as the sequential draws (chi-square tests on first picks and pairs,
+    // tests/test_gpu_parity_bench_sets.py).  The warp ranks the keys all against all (lane L owns moves L, L+32, ...) and
+    // lane j receives the move of rank nexp + j through the warp's shared staging list.  Called by the whole warp.
+    // (out of line: only Policy.random runs it)
+    __device__ __noinline__ static int random_order(Ctx& gx, int k, int nexp, int m, int j, uint64_t key, int lane) {
+        constexpr int Q = (ZC_MAX_MOVES + 31) / 32;
+        uint32_t c[Q];
+        int rank[Q];
+        const int q_used = (k + 31) >> 5;
+#pragma unroll
+        for (int q = 0; q < Q; ++q) {
+            const int i = lane + 32 * q;
+            c[q] = i < k ? (((uint32_t)rng_mix(key ^ (0xD1B54A32D192ED03ull * (uint64_t)(i + 1))) & 0xFFFFFF00u) | (uint32_t)i) : 0xFFFFFFFFu;
+            rank[q] = 0;
+        }
+#pragma unroll
+        for (int qs = 0; qs < Q; ++qs) {
+            if (qs < q_used) {
+                for (int src = 0; src < 32; ++src) {
+                    const uint32_t other = __shfl_sync(FULL_MASK, c[qs], src);
+#pragma unroll
+                    for (int q = 0; q < Q; ++q) rank[q] += other < c[q] ? 1 : 0;
+                }
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < Q; ++q) {
+            const int r = rank[q] - nexp;
+            if (lane + 32 * q < k && r >= 0 && r < m) gx.wmoves[r] = (uint16_t)(lane + 32 * q);
+        }
+        __syncwarp();
+        const int mine = (j >= 0 && j < m) ? (int)gx.wmoves[j] : 0;
+        __syncwarp();
+        return mine;
+    }
     // Policy.immediate_value (policy_functions.py:14-17) as mcts.cpp:65-78 applies it: every expansion of a node
     // picks uniformly among its untried moves whose capture value move[1] is >= (best untried value - freedom).
     // Which move the t-th expansion of a node picks is a function of the node (its key seeds the draws), so the
     // warp replays picks 0 .. nexp+m-1 (lane L owns moves L, L+32, ...) and lane j receives the move of
     // expansion nexp + j.  Called by the whole warp.
-    // With freedom = +inf every untried move is a candidate: that is Policy.random (policy_functions.py:10-12).
-    // (out of line: only the two randomised policies run it)
+    // (out of line: only Policy.immediate_value runs it)
     __device__ __noinline__ static int immediate_value_order(const uint4* node, const State& st, int k, int nexp, int m, int j, float freedom,
                                           uint64_t key, int lane) {
         constexpr int Q = (ZC_MAX_MOVES + 31) / 32;

@@ -424,9 +424,10 @@ ZC_D bool expand_lazy(const SearchParams& p, typename G::Ctx& gx, uint4* __restr
         typename G::State cs = Pst;
         uint32_t cmisc = 0;
         int ei_iv = 0;
-        // random / immediate_value: the warp replays the node's pick process (uniform among the untried moves, resp.
-        // among those within policy_freedom of the best untried capture value)
-        if (p.policy >= 2) ei_iv = G::immediate_value_order(arena + P, Pst, Pk, Pnexp, m, j, p.policy == 3 ? p.policy_freedom : CUDART_INF_F, nkey, lane);
+        // random: the node's keyed uniformly random order; immediate_value: the warp replays the node's pick process (uniform
+        // among the untried moves within policy_freedom of the best untried capture value)
+        if (p.policy == 2) ei_iv = G::random_order(gx, Pk, Pnexp, m, j, nkey, lane);
+        else if (p.policy == 3) ei_iv = G::immediate_value_order(arena + P, Pst, Pk, Pnexp, m, j, p.policy_freedom, nkey, lane);
         if (act) {
             ei = p.policy >= 2 ? ei_iv : expansion_order(p.policy, Pk, Pnexp + j, nkey);
             cs = G::child(Pst, Pmisc, arena + P, Pk, ei, cmisc);
