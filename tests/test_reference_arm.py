@@ -80,7 +80,7 @@ def test_pool_rate_excludes_startup():
         pool.close()
     assert det["sims"] % 200 == 0 and det["sims"] > 0
     assert 0.5 <= det["longest_worker_s"] < 1.5
-    assert rate > 0 and 0.5 < rate2 / rate < 2.0
+    assert rate > 0 and 0.33 < rate2 / rate < 3.0          # two steps of the same pool measure the same thing (start-up is outside both)
 
 
 def test_both_arms_print_the_same_config():

@@ -103,19 +103,24 @@ class DeviceSelfPlay:
             started, finished = n_slots, 0
             results = [None] * total_games
             traj = [[self.init_rec[0].copy()] for _ in range(total_games)] if record else None
-            active = list(range(n_slots))
+            active = np.arange(n_slots, dtype=np.int64)
+            ones_all = torch.ones(n_slots, dtype=torch.uint8, device=dev)
+            init_dev = torch.from_numpy(self.init_rec.view(np.uint8).reshape(1, item).copy()).to(dev)
             plies = 0
             t0 = time.time()
-            while active:
-                idx = torch.tensor(active, dtype=torch.long, device=dev)
-                roots = states_all.index_select(0, idx).contiguous()
+            while len(active):
                 n = len(active)
+                # every slot busy (the steady state while games are being refilled): work on the slot arrays in place;
+                # otherwise gather the running games' rows, and scatter them back after the move
+                whole = n == n_slots
+                idx = None if whole else torch.from_numpy(active).to(dev)
+                roots = states_all if whole else states_all.index_select(0, idx).contiguous()
                 ts.set_roots_dev(roots.data_ptr(), n, stream)
                 if self.kind == "builtin":
                     ts.run(simulations, c, self.batch_size, self.ev, self.pol, seed + plies, stream)
                 else:
                     ts.run_network(self.ev, simulations, c, self.batch_size, self.pol, seed + plies)
-                ones = torch.ones(n, dtype=torch.uint8, device=dev)
+                ones = ones_all[:n]
                 res = np.zeros(n, dtype=np.int32)
                 mv = np.zeros(n, dtype=_ffi.CHESS_MOVE_DTYPE)
                 if chess:
@@ -125,12 +130,13 @@ class DeviceSelfPlay:
                         grown = torch.zeros((n_slots, 2, 2 * hist_cap, 8), dtype=torch.uint8, device=dev)
                         grown[:, :, :hist_cap] = hist_all
                         hist_all, hist_cap = grown, 2 * hist_cap
-                    hist = hist_all.index_select(0, idx).contiguous()
-                    hlen = hlen_all.index_select(0, idx).contiguous()
+                    hist = hist_all if whole else hist_all.index_select(0, idx).contiguous()
+                    hlen = hlen_all if whole else hlen_all.index_select(0, idx).contiguous()
                     _ffi.check(_ffi.lib().zc_search_advance(ts._h, roots.data_ptr(), ones.data_ptr(), hist.data_ptr(), hlen.data_ptr(),
                                                            hist_cap, res.ctypes.data_as(C.c_void_p), mv.ctypes.data_as(C.c_void_p), stream))
-                    hist_all.index_copy_(0, idx, hist)
-                    hlen_all.index_copy_(0, idx, hlen)
+                    if not whole:
+                        hist_all.index_copy_(0, idx, hist)
+                        hlen_all.index_copy_(0, idx, hlen)
                 else:
                     _ffi.check(_ffi.lib().zc_search_advance(ts._h, roots.data_ptr(), ones.data_ptr(), None, None, 0,
                                                            res.ctypes.data_as(C.c_void_p), mv.ctypes.data_as(C.c_void_p), stream))
@@ -139,9 +145,9 @@ class DeviceSelfPlay:
                 new_host = roots.cpu().numpy().view(self.init_rec.dtype).reshape(n) if record else None
                 # bookkeeping per ply, vectorised: which games ended, which slots get the next game (refill
                 # semantics of simulate_games, scripts/train.py:151-170)
-                act = np.asarray(active, dtype=np.int64)
+                act = active
                 if record:
-                    for j, slot in enumerate(active):
+                    for j, slot in enumerate(active.tolist()):
                         traj[slot_game[slot]].append(new_host[j].copy())
                 done = np.nonzero(res != _ffi.RESULT_ONGOING)[0]
                 keep = np.ones(n, dtype=bool)
@@ -157,14 +163,14 @@ class DeviceSelfPlay:
                         refill.append(int(j))
                     else:
                         keep[j] = False
-                still = act[keep].tolist()
-                states_all.index_copy_(0, idx, roots)
+                if not whole:
+                    states_all.index_copy_(0, idx, roots)
                 if refill:
-                    ridx = idx[torch.tensor(refill, dtype=torch.long, device=dev)]
-                    states_all[ridx] = torch.from_numpy(self.init_rec.view(np.uint8).reshape(1, item).copy()).to(dev)
+                    ridx = torch.from_numpy(act[np.asarray(refill, dtype=np.int64)]).to(dev)
+                    states_all[ridx] = init_dev
                     if chess:
                         hlen_all[ridx] = 0
-                active = still
+                active = act[keep]
             torch.cuda.synchronize()
             dt = time.time() - t0
         out = {"results": results, "moves": plies, "seconds": dt, "games_per_hour": total_games / dt * 3600.0,
