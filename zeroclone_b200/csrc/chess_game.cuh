@@ -7,7 +7,10 @@
 namespace zc {
 
 struct ChessGame {
-    static constexpr int kMinBlocks = 8;   // resident 128-thread blocks per SM the fused search is compiled for
+#ifndef ZC_CHESS_MINB
+#define ZC_CHESS_MINB 7
+#endif
+    static constexpr int kMinBlocks = ZC_CHESS_MINB;   // resident 128-thread blocks per SM the fused search is compiled for
     using State = chess::Board;
     static constexpr int SS = 2;             // four bit planes = 32 bytes
     static constexpr int FIRST_SLOTS = 32;   // header + state + first 29 edges in one warp load
@@ -171,7 +174,10 @@ struct ChessGame {
     static constexpr bool kLazyMoves = true;    // leaves are stubs; moves are generated when a node is first expanded
     // the move list of ONE position by the whole warp, left contiguous in the warp's shared-memory staging list
     // (out of line: three call sites, and the generator is the largest piece of code in the kernel)
-    __device__ __noinline__ static int moves_warp(Ctx& gx, const State& s, uint32_t misc, int lane, bool any_only = false) {
+#ifndef ZC_AB_MOVES_ATTR
+#define ZC_AB_MOVES_ATTR __noinline__
+#endif
+    __device__ ZC_AB_MOVES_ATTR static int moves_warp(Ctx& gx, const State& s, uint32_t misc, int lane, bool any_only = false) {
         return chess::generate_warp(s, (int)(misc & chess::MISC_TURN), gx.wmoves, 1, lane, any_only);
     }
     // ... and packed into a node's move slots by the whole warp (8 moves per slot)

@@ -355,8 +355,11 @@ ZC_D void write_priors(uint4* node, const typename G::State& st, int k, int prio
 }
 
 // Turn the stub at `node` into a complete node; returns its (possibly new) slot in `node` and its k.
+#ifndef ZC_AB_MAT_ATTR
+#define ZC_AB_MAT_ATTR __noinline__
+#endif
 template <class G>
-__device__ __noinline__ bool materialize(const SearchParams& p, typename G::Ctx& gx, uint4* __restrict__ arena, TreeCtl& ctl, int lane,
+__device__ ZC_AB_MAT_ATTR bool materialize(const SearchParams& p, typename G::Ctx& gx, uint4* __restrict__ arena, TreeCtl& ctl, int lane,
                       uint32_t& node, const typename G::State& st, uint32_t misc, int& k_out, bool with_priors = false) {
     const uint4 sh = arena[node];
     const int k = G::moves_warp(gx, st, misc, lane);
@@ -627,7 +630,10 @@ ZC_D void backprop_exact(uint4* __restrict__ arena, const uint2* __restrict__ pa
 // ---------------------------------------------------------------------------------------------
 // kernels
 // ---------------------------------------------------------------------------------------------
-constexpr int SEARCH_BLOCK = 128;
+#ifndef ZC_SEARCH_BLOCK
+#define ZC_SEARCH_BLOCK 128
+#endif
+constexpr int SEARCH_BLOCK = ZC_SEARCH_BLOCK;
 
 // Fused persistent search with a built-in evaluator: the whole simulation loop of get_move
 // (mcts.cpp:129-149) for every tree.  Warps pull tree indices from a global counter.

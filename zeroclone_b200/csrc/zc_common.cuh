@@ -6,7 +6,10 @@
 #define ZC_HD __host__ __device__ __forceinline__
 #define ZC_D __device__ __forceinline__
 // one out-of-line copy per kernel: bodies that are large and have several call sites (instruction-cache footprint)
-#define ZC_HD_CALL __host__ __device__ __noinline__
+#ifndef ZC_AB_CALL_ATTR
+#define ZC_AB_CALL_ATTR __noinline__
+#endif
+#define ZC_HD_CALL __host__ __device__ ZC_AB_CALL_ATTR
 #else
 #define ZC_HD inline
 #define ZC_D inline
