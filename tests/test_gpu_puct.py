@@ -108,3 +108,48 @@ def test_engine_config_selects_puct():
     assert st["visits"].tolist() == o.Na and st["best"] == o.best
     with pytest.raises(ValueError):
         Engine(dict(cfg, mcts={"select": "alphabeta"}))
+
+
+def test_chess_puct_split_phase_matches_oracle():
+    """external-evaluator kernels in PUCT mode on chess, with material read back from the packed planes (exact in fp32)"""
+    vals = torch.tensor([1, 3, 3, 5, 9, 0, -1, -3, -3, -5, -9, 0], dtype=torch.float32, device="cuda")
+
+    class Material:
+        dtype = torch.float16
+
+        def __call__(self, planes, out):
+            mat = (planes[:, :12].float().sum(dim=(2, 3)) * vals).sum(dim=1)
+            out.copy_(mat * (2 * planes[:, 12, 0, 0].float() - 1))
+            return out
+
+    pv = {ord(k): v for k, v in {'P': 1, 'N': 3, 'B': 3, 'R': 5, 'Q': 9, 'p': -1, 'n': -3, 'b': -3, 'r': -5, 'q': -9}.items()}
+
+    def ext(states_u8):
+        out = np.zeros(len(states_u8))
+        for i, s in enumerate(states_u8):
+            out[i] = (1 - 2 * int(s[64])) * sum(pv.get(int(b), 0) for b in s[:64])
+        return out
+
+    roots = chess_roots_set_b(16)
+    sims = 300
+    ts = TreeSearch(_ffi.GAME_CHESS, len(roots), sims)
+    ts.set_mode(_ffi.SELECT_PUCT, 1.0, 1)
+    ts.set_roots(roots)
+    ts.run_network(Material(), sims, 10.0, 32, _ffi.POLICY_FIRST)
+    out, hashes = ts.results(), ts.tree_hash()
+    for i, rec in enumerate(roots):
+        check(out, hashes, i, zo.search_puct(zo.GAME_CHESS, chess_oracle_state(rec), sims, 10.0, 32, zo.EVAL_EXTERNAL, 1.0, 1, external=ext))
+
+
+def test_device_selfplay_in_puct_mode_finishes_games():
+    from zeroclone_b200 import mcts
+    from zeroclone_b200.games.connect4 import c4_backend
+    from zeroclone_b200.policy_functions import Policy
+    from zeroclone_b200.selfplay import DeviceSelfPlay
+    from zeroclone_b200.value_functions import Value
+    sp = DeviceSelfPlay(c4_backend, Value("c4_positional"), Policy("random"), n_slots=64, device=0,
+                        mode=mcts.select_mode({"select": "puct", "virtual_loss": 1.0}))
+    out = sp.play(96, 200, 1.4, seed=3, record=True)
+    assert len(out["results"]) == 96 and all(r in (-1, 0, 1) for r in out["results"])
+    planes, labels = out["dataset"]
+    assert planes.shape[1:] == (2, 6, 7) and len(planes) == len(labels) == out["moves"] + 96
