@@ -21,7 +21,7 @@ each with value, e2e, roofline, clocks (and cpu_baseline at N = 1).
 Keys beyond the base contract: roofline (dominant kernel), roofline_tree (our tree kernels), cpu_baseline (the
 reference's CPU path timed on this box's host cores, N=1 only), e2e (host buffers in, host results out), gpu_launches,
 clocks, selfplay (games/hour, device-resident move loop).
-`--impl reference` times the reference's own CPU implementation (oracle/_ref/pyref: its compiled mcts / chess modules
+`--impl reference` times the reference's own CPU implementation (oracle/_ref/pyref.zip: its compiled mcts / chess modules
 and its stock value_functions.py / c4_backend.py) on every host core over a bounded sample of the same workload; the
 clock runs inside persistent workers after their imports and model construction (oracle/ref_harness.py).
 """
@@ -561,7 +561,7 @@ def cpu_baseline(name: str, sims: int, budget_s: float = 15.0) -> dict:
 
 def run_reference(args):
     """`--impl reference`: the reference's own CPU implementation of the path.  No torch, no CUDA, no libzc_b200 in
-    this process; the workers import the reference's files from oracle/_ref/pyref."""
+    this process; the workers import the reference's files from oracle/_ref/pyref.zip (unpacked to a temporary directory)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -597,7 +597,7 @@ def run_reference(args):
                   "value = sum of the workers' own sims/s, clock inside the workers after imports and model construction")
     line = dict(base, value=v, ms_per_step=ms,
                 note="reference mcts.get_move (engine/mcts/src/mcts.cpp compiled unmodified) with the reference's stock Value / backend "
-                     "Python files (oracle/_ref/pyref) on every host core, CUDA hidden (DEVICE=cpu, fp32); bounded sample of the workload",
+                     "Python files (oracle/_ref/pyref.zip) on every host core, CUDA hidden (DEVICE=cpu, fp32); bounded sample of the workload",
                 cpu_baseline={"value": v, "unit": "sims/s", "cores": cores, "kind": kind, "sample": sample},
                 e2e={"value": v, "unit": "sims/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0})
     print(json.dumps(line))

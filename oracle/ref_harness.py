@@ -1,10 +1,11 @@
 """TEST/BENCH INFRASTRUCTURE: drive the UNMODIFIED reference on the box's host cores.
 
-`make -C oracle ref` lays the reference's own files of the hot path out under oracle/_ref/pyref/
-as its `engine` and `models` packages: the two pybind11 modules compiled from its C++ sources
+`make -C oracle ref` packs the reference's own files of the hot path into oracle/_ref/pyref.zip as its
+`engine` and `models` packages: the two pybind11 modules compiled from its C++ sources
 (engine/mcts/src/*.cpp, engine/games/chess/src/*.cpp) and, verbatim, engine/value_functions.py,
 engine/policy_functions.py, engine/games/connect4/c4_backend.py, engine/mcts/__init__.py and
-models/.  This file imports THOSE (never this repo's packages, never libzc_b200.so) and runs
+models/ (build output: git-ignored, unpacked into a temporary directory at run time).  This file
+imports THOSE (never this repo's packages, never libzc_b200.so) and runs
 `engine.mcts.get_move(state, Value, policy, backend, sims, c, batch)` -- the call
 engine/engine.py:119-129 makes -- one tree at a time on every host core.
 
@@ -33,14 +34,36 @@ import time
 import numpy as np
 
 _REF_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
-PYREF = os.path.join(_REF_DIR, "pyref")
+PYREF_ZIP = os.path.join(_REF_DIR, "pyref.zip")
+PYREF = None            # where the archive is unpacked for this process tree (pyref_dir())
 C_UCT, BATCH = 1.4, 32
 
 
 def ref_available() -> bool:
-    d = os.path.join(PYREF, "engine", "mcts")
-    return (os.path.isdir(d) and any(f.startswith("mcts") and f.endswith(".so") for f in os.listdir(d))
-            and os.path.exists(os.path.join(PYREF, "engine", "value_functions.py")))
+    return os.path.exists(PYREF_ZIP)
+
+
+def pyref_dir() -> str:
+    """Unpack oracle/_ref/pyref.zip (the reference's own files, packed by `make -C oracle ref`) into a temporary directory
+    named after the archive's digest; compiled modules cannot be imported from inside a zip.  Idempotent and race-free."""
+    global PYREF
+    if PYREF is None:
+        import hashlib
+        import tempfile
+        import zipfile
+        digest = hashlib.sha256(open(PYREF_ZIP, "rb").read()).hexdigest()[:16]
+        target = os.path.join(tempfile.gettempdir(), f"zc_pyref_{digest}")
+        if not os.path.exists(os.path.join(target, "SHA256SUMS")):
+            tmp = tempfile.mkdtemp(prefix="zc_pyref_unpack_")
+            with zipfile.ZipFile(PYREF_ZIP) as z:
+                z.extractall(tmp)
+            try:
+                os.rename(tmp, target)              # atomic: a concurrent worker either wins or finds it there
+            except OSError:
+                import shutil
+                shutil.rmtree(tmp, ignore_errors=True)
+        PYREF = target
+    return PYREF
 
 
 def ref_modules():
@@ -63,9 +86,10 @@ def stock(need_torch: bool = False) -> _Stock:
     """Import the reference's own `engine` / `models` packages from oracle/_ref/pyref.  This repo ships
     import aliases of the same names at its root (drop-in for users); they must not win here."""
     global _stock
+    PYREF = pyref_dir() if ref_available() else ""
     if _stock is None:
         if not ref_available():
-            raise ImportError("oracle/_ref/pyref is missing: run `make -C oracle ref` where /root/reference exists")
+            raise ImportError("oracle/_ref/pyref.zip is missing: run `make -C oracle ref` where /root/reference exists")
         for name in list(sys.modules):
             if name in ("engine", "models") or name.startswith(("engine.", "models.")):
                 f = getattr(sys.modules[name], "__file__", None) or ""

@@ -1,5 +1,5 @@
 """The reference arm of bench.py (`--impl reference`, cpu_baseline) drives the reference's STOCK files laid out by
-`make -C oracle ref` under oracle/_ref/pyref.  CPU-only checks: the stock files are the ones imported, the root sets
+`make -C oracle ref` into oracle/_ref/pyref.zip (unpacked to a temporary directory at run time).  CPU-only checks: the stock files are the ones imported, the root sets
 the reference's own backends generate are the ones the GPU arm searches, both arms print the same `config`, and the
 worker pool times searches (not start-up)."""
 import hashlib
@@ -14,7 +14,7 @@ sys.path.insert(0, REPO)
 
 from oracle import ref_harness as rh  # noqa: E402
 
-pytestmark = pytest.mark.skipif(not rh.ref_available(), reason="oracle/_ref/pyref not built (needs /root/reference)")
+pytestmark = pytest.mark.skipif(not rh.ref_available(), reason="oracle/_ref/pyref.zip not built (needs /root/reference)")
 
 
 def _stock_in_subprocess(code: str) -> str:
@@ -27,10 +27,11 @@ def _stock_in_subprocess(code: str) -> str:
 
 
 def test_pyref_files_are_the_reference_files():
-    sums = dict(line.split()[::-1] for line in open(os.path.join(rh.PYREF, "SHA256SUMS")).read().splitlines())
+    root = rh.pyref_dir()
+    sums = dict(line.split()[::-1] for line in open(os.path.join(root, "SHA256SUMS")).read().splitlines())
     assert "engine/value_functions.py" in sums and "engine/games/connect4/c4_backend.py" in sums
     for rel, want in sums.items():
-        got = hashlib.sha256(open(os.path.join(rh.PYREF, rel), "rb").read()).hexdigest()
+        got = hashlib.sha256(open(os.path.join(root, rel), "rb").read()).hexdigest()
         assert got == want, rel
         ref = os.path.join("/root/reference", rel)
         if os.path.exists(ref):           # dev container: byte-identical to the checkout
@@ -57,7 +58,7 @@ def test_stock_modules_and_values():
     out = _stock_in_subprocess(
         "from oracle import ref_harness as rh\n"
         "s = rh.stock(need_torch=True)\n"
-        "assert s.vf.__file__.startswith(rh.PYREF) and s.c4.__file__.startswith(rh.PYREF)\n"
+        "assert s.vf.__file__.startswith(rh.pyref_dir()) and s.c4.__file__.startswith(rh.pyref_dir())\n"
         "assert s.vf.DEVICE == 'cpu'\n"
         "import sys; assert 'zeroclone_b200' not in sys.modules and not any('libzc_b200' in l for l in open('/proc/self/maps'))\n"
         "v = rh.make_value('connect4', 'c4_positional'); b = s.c4\n"
