@@ -210,6 +210,8 @@ ZC_D bool expand_spine(const SearchParams& p, typename G::Ctx& gx, uint4* __rest
                        TreeCtl& ctl, int B, int lane, uint32_t P, const uint4& hdr, const typename G::State& Pst,
                        int d0, WarpPlan& wp, int& D_out, Leaf<G>& leaf) {
     const uint64_t tkey = p.seed ^ ((uint64_t)ctl.tree_id << 32);
+    const bool keyed = p.policy >= 2;                          // only the randomised policies order moves by a node key,
+    const bool drawn = p.evaluator == ZC_EVAL_C4_ROLLOUT;      // only the rollout evaluator draws random numbers
     typename G::State Sg = Pst;
     uint32_t Mg = hdr_misc(hdr);
     const int k0 = (int)hdr_k(hdr);
@@ -246,7 +248,7 @@ ZC_D bool expand_spine(const SearchParams& p, typename G::Ctx& gx, uint4* __rest
         // the node is fully expanded and simulations remain: every fresh child has UCT = +inf, the lowest
         // move index among them wins (mcts.cpp:43,57)
         int e_star, j_star;
-        lowest_fresh(p.policy, kg, nexpg, m, rng_mix(tkey ^ G::state_key(Sg, Mg)), lane, e_star, j_star);
+        lowest_fresh(p.policy, kg, nexpg, m, keyed ? rng_mix(tkey ^ G::state_key(Sg, Mg)) : 0ull, lane, e_star, j_star);
         const int next_lane = made - m + j_star;
         if (g == 0) P_e = e_star;
         else if (lane == spine_lane) my_spine_e = e_star;
@@ -271,14 +273,14 @@ ZC_D bool expand_spine(const SearchParams& p, typename G::Ctx& gx, uint4* __rest
     uint32_t cmisc = myPm;
     double val = 0.0;
     if (is_leaf) {
-        ei = expansion_order(p.policy, myk, mynexp + myj, rng_mix(tkey ^ G::state_key(myP, myPm)));
+        ei = expansion_order(p.policy, myk, mynexp + myj, keyed ? rng_mix(tkey ^ G::state_key(myP, myPm)) : 0ull);
         cs = G::child(myP, myPm, nullptr, myk, ei, cmisc);
         ck = G::count_moves(gx, cs, cmisc);
         if (kBuiltinEval)
-            val = G::eval_child(cs, cmisc, ck, p.evaluator, rng_mix(tkey ^ G::state_key(cs, cmisc) ^ ((uint64_t)ctl.sims_done << 40) ^ 0x51ull));
+            val = G::eval_child(cs, cmisc, ck, p.evaluator, drawn ? rng_mix(tkey ^ G::state_key(cs, cmisc) ^ ((uint64_t)ctl.sims_done << 40) ^ 0x51ull) : 0ull);
     } else if (is_self) {
         if (kBuiltinEval)
-            val = G::eval(myP, myPm, p.evaluator, rng_mix(tkey ^ G::state_key(myP, myPm) ^ ((uint64_t)ctl.sims_done << 40) ^ ((uint64_t)lane << 8)));
+            val = G::eval(myP, myPm, p.evaluator, drawn ? rng_mix(tkey ^ G::state_key(myP, myPm) ^ ((uint64_t)ctl.sims_done << 40) ^ ((uint64_t)lane << 8)) : 0ull);
     }
     const int csize = is_leaf ? 1 + G::SS + ck + G::move_slots(ck) : 0;
     int total;
@@ -422,7 +424,7 @@ ZC_D bool expand_lazy(const SearchParams& p, typename G::Ctx& gx, uint4* __restr
         const int m = min(Pk - Pnexp, B - made);
         const int j = lane - made;
         const bool act = j >= 0 && j < m;
-        const uint64_t nkey = rng_mix(tkey ^ G::state_key(Pst, Pmisc));
+        const uint64_t nkey = p.policy >= 2 ? rng_mix(tkey ^ G::state_key(Pst, Pmisc)) : 0ull;      // only the randomised policies are keyed
         int ei = 0x7FFFFFFF;
         typename G::State cs = Pst;
         uint32_t cmisc = 0;
