@@ -175,6 +175,13 @@ class FusedTowerEvaluator:
         except Exception:
             pass
 
+    def fault(self) -> int:
+        """0, or 0x80000000 | wait tag if the kernel gave up on one of its bounded barrier waits (a protocol bug, never expected);
+        readable even after the CUDA context has been poisoned by the trap (the word lives in pinned host memory).  Clears it."""
+        from . import _ffi
+
+        return int(_ffi.lib().zc_tower_fault(self._h)) if getattr(self, "_h", None) else 0
+
     @property
     def launches(self) -> int:
         from . import _ffi
