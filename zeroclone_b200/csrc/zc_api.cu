@@ -409,6 +409,7 @@ extern "C" int zc_search_create(int game, int device, int max_trees, int max_sim
 extern "C" int zc_search_destroy(zc_search* h) {
     if (!h) return ZC_OK;
     cudaSetDevice(h->device);
+    if (h->copy_stream) cudaStreamSynchronize(h->copy_stream);      // a readout copy may still be in flight
     cudaFree(h->arena);
     cudaFree(h->ctl);
     cudaFree(h->path);
