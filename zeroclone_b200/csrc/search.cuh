@@ -78,14 +78,13 @@ ZC_HD uint64_t rng_mix(uint64_t z) {
     return z ^ (z >> 31);
 }
 
-// Keyed uniformly random ordering of [0,k), k <= 16: element j of a Fisher-Yates shuffle whose t-th draw is a
-// pure function of (key, t).  Used for Policy.random (policy_functions.py:10-12) on nodes with few moves (Connect
+// Keyed uniformly random ordering of [0,k), k <= 8: element j of a Fisher-Yates shuffle whose draws are the
+// mixed-radix digits of one hash of the key.  Used for Policy.random (policy_functions.py:10-12) on nodes with few moves (Connect
 // Four: k <= 7): expanding moves in the order perm(0), perm(1), ... draws each next move uniformly from the untried
-// ones, which is what random.choice on the untried list does -- exactly, not approximately: pick t takes the
-// (draw_t mod (k - t))-th of the remaining elements (chi-square tests on first picks and on pairs,
-// tests/test_gpu_parity_bench_sets.py).  The remaining elements live as 4-bit entries of one 64-bit word.
-// Wider nodes (chess) replay the same process warp-cooperatively: ChessGame::immediate_value_order.
-constexpr int KEYED_PERM_MAX = 16;
+// ones, which is what random.choice on the untried list does: pick t takes the (digit t)-th of the remaining elements (chi-square tests on first picks and on pairs,
+// tests/test_gpu_parity_bench_sets.py).  The remaining elements live as 4-bit entries of one 32-bit word.
+// Wider nodes (chess) order their moves by per-move hash keys instead: ChessGame::random_order.
+constexpr int KEYED_PERM_MAX = 8;
 ZC_HD uint64_t pick_draw(uint64_t key, int t) { return rng_mix(key ^ (0x9E3779B97F4A7C15ull * (uint64_t)(t + 1))); }
 // (out of line: only Policy.random runs it, and inlined it costs the deterministic policies registers)
 #ifdef __CUDACC__
@@ -95,13 +94,18 @@ inline
 #endif
 int keyed_perm(int k, int j, uint64_t key) {
     if (k <= 1) return 0;
-    uint64_t rest = 0xFEDCBA9876543210ull;
+    // one hash per node; the draws are the mixed-radix digits (radices k, k-1, ...) of its high 32 bits: k! <= 8! = 40320, so
+    // every draw is uniform up to a relative bias below 2^-16 (Connect Four's 7 moves: 2^-19) -- and the divisions are 32-bit
+    uint32_t w = (uint32_t)(rng_mix(key) >> 32);
+    uint32_t rest = 0x76543210u;                                   // the moves not yet drawn, four bits each
     int pick = 0;
     for (int t = 0; t <= j; ++t) {
-        const int r = (int)((uint32_t)(pick_draw(key, t) >> 32) % (uint32_t)(k - t));
-        pick = (int)((rest >> (4 * r)) & 0xFull);
-        const uint64_t low = r ? rest & ((1ull << (4 * r)) - 1ull) : 0ull;
-        rest = low | ((rest >> (4 * r + 4)) << (4 * r));          // drop entry r
+        const uint32_t radix = (uint32_t)(k - t);
+        const int d = (int)(w % radix);
+        w /= radix;
+        pick = (int)((rest >> (4 * d)) & 0xFu);
+        const uint32_t low = d ? rest & ((1u << (4 * d)) - 1u) : 0u;
+        rest = d < 7 ? low | ((rest >> (4 * d + 4)) << (4 * d)) : low;      // drop entry d
     }
     return pick;
 }
