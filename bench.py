@@ -519,17 +519,45 @@ def _port_rate(name: str, sims: int, budget_s: float):
 
 def _port_worker(job):
     name, seed, sims, budget = job
+    import numpy as np
     from oracle import zc_oracle as zo
     wl = WORKLOADS[name]
+    chess = wl["game"] == "chess"
+    ext = None
+    if wl["evaluator"] == "value_net":      # the port's search around this repo's PyTorch module in fp32 on one core
+        import torch
+        torch.set_num_threads(1)
+        if chess:
+            from zeroclone_b200.models.chess_value.network import ValueNetwork
+        else:
+            from zeroclone_b200.models.connect4_value.network import ValueNetwork
+        torch.manual_seed(0)
+        model = ValueNetwork().eval()
+
+        def ext(states_u8):
+            k = states_u8.shape[0]
+            if chess:
+                planes = np.zeros((k, 17, 8, 8), dtype=np.float32)
+                board = states_u8[:, :64].reshape(k, 8, 8)
+                for p_, ch in enumerate(b"PNBRQKpnbrqk"):
+                    planes[:, p_] = board == ch
+                planes[:, 12] = (states_u8[:, 64] == 0)[:, None, None]
+                for f in range(4):
+                    planes[:, 13 + f] = (states_u8[:, 66 + f] != 0)[:, None, None]
+            else:
+                cells = states_u8[:, :42].reshape(k, 6, 7)
+                turn = states_u8[:, 44]
+                cur = np.where(turn == 0, ord('X'), ord('O'))[:, None, None]
+                opp = np.where(turn == 0, ord('O'), ord('X'))[:, None, None]
+                planes = np.stack([cells == cur, cells == opp], axis=1).astype(np.float32)
+            with torch.no_grad():
+                return model(torch.from_numpy(planes)).view(-1).double().numpy()
+    ev = zo.EVAL_EXTERNAL if ext else (zo.EVAL_CHESS_CRUDE if chess else zo.EVAL_C4_POSITIONAL)
     done, t0 = 0, time.perf_counter()
     i = seed * 131
     while True:
-        if wl["game"] == "chess":
-            st = zo.ch_init()
-            zo.search(zo.GAME_CHESS, st, sims, C_UCT, BATCH, zo.EVAL_CHESS_CRUDE, zo.POLICY_FIRST)
-        else:
-            st = zo.c4_from_moves([(i + j) % 7 for j in range(i % 9)])
-            zo.search(zo.GAME_C4, st, sims, C_UCT, BATCH, zo.EVAL_C4_POSITIONAL, zo.POLICY_FIRST)
+        st = zo.ch_init() if chess else zo.c4_from_moves([(i + j) % 7 for j in range(i % 9)])
+        zo.search(zo.GAME_CHESS if chess else zo.GAME_C4, st, sims, C_UCT, BATCH, ev, zo.POLICY_FIRST, external=ext)
         i += 1
         done += sims
         dt = time.perf_counter() - t0
