@@ -8,7 +8,7 @@ namespace zc {
 
 struct ChessGame {
 #ifndef ZC_CHESS_MINB
-#define ZC_CHESS_MINB 7
+#define ZC_CHESS_MINB 8
 #endif
     static constexpr int kMinBlocks = ZC_CHESS_MINB;   // resident 128-thread blocks per SM the fused search is compiled for
     using State = chess::Board;
