@@ -202,3 +202,19 @@ def test_engine_with_immediate_value_policy_on_device():
     c4 = Engine({"game": "connect4", "backend": "c4_backend", "value_function": "c4_terminal", "threads": 2,
                  "policy_functions": "immediate_value"})
     assert c4.play_mcts(0, 64, 1.4) is None      # all Connect Four moves carry value 0: same as random
+
+
+def test_shipped_chess_value_config_at_its_own_size():
+    """configs/chess_value.yaml as shipped by the reference: 10 games, 50 000 simulations per move, network evaluator, random
+    expansion policy.  One move for every game through the Engine API: no arena overflow, every root fully searched."""
+    import os
+    from zeroclone_b200.engine import Engine
+    eng = Engine(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "configs", "chess_value.yaml"))
+    sims = eng.config["mcts"]["simulations"]
+    assert eng.threads == 10 and sims == 50000
+    res = eng.play_mcts_parallel(range(eng.threads), simulations=sims, c=eng.config["mcts"]["c_puct"])
+    assert set(res) == set(range(10)) and all(r is None for r in res.values())         # ten opening moves, games go on
+    for i in range(10):
+        st = eng.last_search_stats(i)
+        assert int(st["visits"].sum()) == sims and st["best"] == int(st["visits"].argmax())
+        assert len(eng.history[i].states) == 2
