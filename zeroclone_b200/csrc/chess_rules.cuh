@@ -510,24 +510,36 @@ __device__ __forceinline__ int generate_warp(const Board& b, int turn, uint16_t*
     }
     const int total = __shfl_sync(0xFFFFFFFFu, x, 31);
     const int pos = x - cnt;
-    uint64_t tg = targets;
-    while (tg) {                                       // any order: every move knows its own index
-        const int t = zc_ctz64(tg);
-        tg &= tg - 1;
-        int rank;
-        if (type == PAWN) {
-            rank = 0;
+    // Emission, any order (every move knows its own index).  With at most 16 pieces a side -- always, in a game -- lanes
+    // 16..31 own no piece: lane L + 16 takes over the upper half of lane L's target squares, so the walk over the set bits is
+    // half as long and 32 bits wide.
+    const bool split = n_own <= 16;
+    const int src = split ? (lane & 15) : lane;
+    const uint64_t e_targets = __shfl_sync(0xFFFFFFFFu, targets, src);
+    const int e_sq = __shfl_sync(0xFFFFFFFFu, sq, src), e_type = __shfl_sync(0xFFFFFFFFu, type, src), e_pos = __shfl_sync(0xFFFFFFFFu, pos, src);
+    const uint32_t e_pawn = __shfl_sync(0xFFFFFFFFu, pawn_order, src);
+#pragma unroll 1
+    for (int half = 0; half < 2; ++half) {
+        if (split && half != (lane >> 4)) continue;
+        uint32_t tg = half ? (uint32_t)(e_targets >> 32) : (uint32_t)e_targets;
+        while (tg) {
+            const int t = (__ffs((int)tg) - 1) + 32 * half;
+            tg &= tg - 1;
+            int rank;
+            if (e_type == PAWN) {
+                rank = 0;
 #pragma unroll
-            for (int q = 0; q < 3; ++q) {              // targets listed before t in the pawn's fixed order
-                const int tq = (int)(pawn_order >> (6 * q)) & 63;
-                if (tq == t) break;
-                rank += (int)(targets >> tq & 1);
+                for (int q = 0; q < 3; ++q) {          // targets listed before t in the pawn's fixed order
+                    const int tq = (int)(e_pawn >> (6 * q)) & 63;
+                    if (tq == t) break;
+                    rank += (int)(e_targets >> tq & 1);
+                }
+            } else {
+                const uint64_t before = e_type == KNIGHT ? bit(t) - 1 : d_before[e_sq][t];
+                rank = zc_popc64(e_targets & before);
             }
-        } else {
-            const uint64_t before = type == KNIGHT ? bit(t) - 1 : d_before[sq][t];
-            rank = zc_popc64(targets & before);
+            out[(size_t)(e_pos + rank) * stride] = pack_move(e_sq, t);
         }
-        out[(size_t)(pos + rank) * stride] = pack_move(sq, t);
     }
     __syncwarp();
     return total;
