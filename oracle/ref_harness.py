@@ -188,7 +188,7 @@ def chess_state_from_bytes(raw: bytes):
 
 
 # ---- evaluators --------------------------------------------------------------------------------
-def make_value(game: str, evaluator: str):
+def make_value(game: str, evaluator: str, allow_cuda: bool = False):
     """A stock `Value` for the workload's evaluator."""
     if evaluator == "value_net":
         s = stock(need_torch=True)
@@ -201,7 +201,7 @@ def make_value(game: str, evaluator: str):
         v = s.Value.__new__(s.Value)         # init_network_latest (value_functions.py:104-112) minus the checkpoint lookup
         v.name, v.init_args = "network_latest", {"batch_size": BATCH}
         v._nn_setup(model, BATCH)
-        assert v.device == "cpu", "the reference arm is the reference's CPU path"
+        assert allow_cuda or v.device == "cpu", "the reference arm is the reference's CPU path"
         return v
     s = stock(need_torch=True)             # value_functions.py imports torch at module level
     if evaluator == "chess_crude":
@@ -222,12 +222,13 @@ def make_value(game: str, evaluator: str):
 
 
 # ---- persistent worker pool --------------------------------------------------------------------
-def _worker_main(conn, game, evaluator, rows, sims):
+def _worker_main(conn, game, evaluator, rows, sims, hide_cuda=True):
     try:
-        os.environ["CUDA_VISIBLE_DEVICES"] = ""        # the reference's Value then picks DEVICE="cpu", fp32
+        if hide_cuda:
+            os.environ["CUDA_VISIBLE_DEVICES"] = ""    # the reference's Value then picks DEVICE="cpu", fp32
         os.environ.setdefault("OMP_NUM_THREADS", "1")
         s = stock(need_torch=True)
-        value = make_value(game, evaluator)
+        value = make_value(game, evaluator, allow_cuda=not hide_cuda)
         if game == "chess":
             backend = s.chess
             states = [chess_state_from_bytes(r) for r in rows]
@@ -260,7 +261,9 @@ def _worker_main(conn, game, evaluator, rows, sims):
 class RefPool:
     """`cores` persistent processes, each owning a slice of the root set.  step(seconds) -> (sims/s, detail)."""
 
-    def __init__(self, game: str, evaluator: str, rows: list, sims: int, cores: int | None = None):
+    def __init__(self, game: str, evaluator: str, rows: list, sims: int, cores: int | None = None, hide_cuda: bool = True):
+        """hide_cuda=False (tools/ref_gpu_net.py only, never the bench arms): the stock Value puts the network on the GPU in
+        fp16 (value_functions.py:5-6) -- how a user of the reference would run it on a GPU box."""
         import multiprocessing as mp
         if cores is None:
             cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
@@ -271,12 +274,14 @@ class RefPool:
         per = max(1, len(rows) // cores)
         self.procs, self.conns = [], []
         saved = {k: os.environ.get(k) for k in ("CUDA_VISIBLE_DEVICES", "OMP_NUM_THREADS", "MKL_NUM_THREADS")}
-        os.environ.update({"CUDA_VISIBLE_DEVICES": "", "OMP_NUM_THREADS": "1", "MKL_NUM_THREADS": "1"})
+        os.environ.update({"OMP_NUM_THREADS": "1", "MKL_NUM_THREADS": "1"})
+        if hide_cuda:
+            os.environ["CUDA_VISIBLE_DEVICES"] = ""
         try:
             for i in range(cores):
                 a, b = ctx.Pipe()
                 mine = rows[i * per:(i + 1) * per] or rows[:1]
-                p = ctx.Process(target=_worker_main, args=(b, game, evaluator, mine, sims), daemon=True)
+                p = ctx.Process(target=_worker_main, args=(b, game, evaluator, mine, sims, hide_cuda), daemon=True)
                 p.start()
                 self.procs.append(p)
                 self.conns.append(a)
