@@ -183,3 +183,29 @@ def test_chess_split_phase_with_exact_evaluator_matches_fused():
         assert out["visits"][i][:o.n_moves].tolist() == o.Na, i
         assert out["value_sums"][i][:o.n_moves].tolist() == o.Wa, i
         assert int(hashes[i]) == o.tree_hash, i
+
+
+def test_warp_generator_on_crowded_and_odd_boards():
+    """Random boards far outside normal play -- up to 30 pieces a side, several kings or none, pawns on the last rows -- so that
+    every branch of the warp generator is taken (more than 16 pieces: no half-warp split of the emission; more than 24: the
+    king's steps are tested by its own lane; more than 32: the serial fallback; no king -- the reference's phantom king at
+    (-1,-1); several kings).  The warp generator,
+    the serial generator and the oracle (the pinned restatement of chess_backend.cpp:184-360) must list the same moves in
+    the same order."""
+    from test_rules_odd_boards import odd_boards
+    boards = [{"board": b.decode(), "turn": t, "fifty": 0, "flags": [0, 0, 0, 0]} for b, t in odd_boards()]
+    arr = states_array(boards)
+    mw, cw, fw = device_legal(arr, warp=True)
+    ms, cs, fs = device_legal(arr, warp=False)
+    assert cw.tolist() == cs.tolist() and fw.tolist() == fs.tolist()
+    crowded = 0
+    for i, rec in enumerate(boards):
+        st = zo.ChState()
+        st.board[:] = rec["board"].encode()
+        st.turn = rec["turn"]
+        want = [[m[0][0], m[0][1], m[0][2], m[0][3], float(m[1])] for m in zo.ch_legal(st)]
+        assert as_lists(mw[i], cw[i]) == want, i
+        assert as_lists(ms[i], cs[i]) == want, i
+        own = sum(1 for ch in rec["board"] if ch != " " and ch.isupper() == (rec["turn"] == 0))
+        crowded += own > 16
+    assert crowded > 100

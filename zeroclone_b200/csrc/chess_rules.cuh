@@ -230,20 +230,41 @@ ZC_HD Sets derive(const Board& b, int turn) {
     return s;
 }
 
-// chess_backend.cpp:345-358 -- make the move, find the mover's (first) king, test it.
-// A side without a king is never "in check" (the reference reads out of range there).
+// A side WITHOUT a king (only a hand-made position): find_king leaves (kr, kc) = (-1, -1) (chess_backend.cpp:68-81) and
+// king_attacked, whose every read is bounds-checked (:85-144), tests that phantom square: what can "attack" it from the board
+// is a pawn on square 0 when black is to move ((kr+1, kc+1), :97), a knight on (0,1) or (1,0), a bishop or queen first
+// on the diagonal (0,0), (1,1), ..., or the enemy king on square 0.  Reproduced as is.
+// (out of line: a kingless side never occurs in play, and the hot paths must not carry this code)
+constexpr uint64_t MAIN_DIAGONAL = 0x8040201008040201ull;
+ZC_HD_CALL bool phantom_king_attacked(int side, uint64_t occ, uint64_t e_pawn, uint64_t e_knight, uint64_t e_diag, uint64_t e_king) {
+    const uint64_t on_diag = occ & MAIN_DIAGONAL;
+    return (((side == 1 ? e_pawn : 0ull) | e_king) & 1ull) != 0 || (e_knight & (bit(1) | bit(8))) != 0 ||
+           ((on_diag & (0 - on_diag)) & e_diag) != 0;
+}
+
+// the make-move test of a kingless side: the phantom square after the move
+ZC_HD_CALL bool kingless_move_ok(uint64_t occ, int turn, int from, int to, uint64_t e_pawn, uint64_t e_knight, uint64_t e_diag, uint64_t e_king) {
+    const uint64_t keep = ~bit(to);
+    return !phantom_king_attacked(turn, (occ & ~bit(from)) | bit(to), e_pawn & keep, e_knight & keep, e_diag & keep, e_king & keep);
+}
+
+// chess_backend.cpp:345-358 -- make the move, find the mover's (first) king, test it.  Precondition: the mover HAS a king
+// (callers route a kingless side to kingless_move_ok).
 ZC_HD bool move_keeps_king_safe(const Sets& s, int turn, int from, int to, bool king_moves) {
     const uint64_t f = bit(from), t = bit(to);
     const uint64_t kings = king_moves ? ((s.own_king & ~f) | t) : s.own_king;
-    if (!kings) return true;
-    const int ksq = zc_ctz64(kings);
     const uint64_t occ = (s.occ & ~f) | t, keep = ~t;
+    const int ksq = zc_ctz64(kings);
     return !square_attacked(turn, ksq, occ, s.e_pawn & keep, s.e_knight & keep, (s.e_bishop | s.e_queen) & keep,
                             (s.e_rook | s.e_queen) & keep, s.e_king & keep);
 }
 ZC_HD bool in_check(const Board& b, int turn) {   // king of the side to move attacked now?
     const Sets s = derive(b, turn);
-    if (!s.own_king) return false;
+    if (!s.own_king) {                            // the phantom square, inline here (a dozen instructions, no call in a hot function)
+        const uint64_t on_diag = s.occ & MAIN_DIAGONAL;
+        return ((((turn == 1 ? s.e_pawn : 0ull) | s.e_king) & 1ull) | (s.e_knight & (bit(1) | bit(8))) |
+                ((on_diag & (0 - on_diag)) & (s.e_bishop | s.e_queen))) != 0;
+    }
     return square_attacked(turn, zc_ctz64(s.own_king), s.occ, s.e_pawn, s.e_knight, s.e_bishop | s.e_queen,
                            s.e_rook | s.e_queen, s.e_king);
 }
@@ -331,9 +352,14 @@ ZC_HD int generate(const Board& b, int turn, uint16_t* out, int stride = 1) {
         }
     }
     // ---- pass 2: legality filter, stable, in place
-    if (!s.own_king) {                       // a side without a king is never "in check"
-        for (int i = 0; i < n; ++i) out[i * stride] &= 0x0FFF;
-        return n;
+    if (!s.own_king) {                       // a side without a king: every move takes the make-move test against the phantom square
+        int m = 0;
+        for (int i = 0; i < n; ++i) {
+            const uint16_t mv = out[i * stride];
+            if (kingless_move_ok(s.occ, turn, mv & 63, (mv >> 6) & 63, s.e_pawn, s.e_knight, s.e_bishop | s.e_queen, s.e_king))
+                out[(m++) * stride] = (uint16_t)(mv & 0x0FFF);
+        }
+        return m;
     }
     const int ksq = zc_ctz64(s.own_king);    // find_king: the first king in index order (:68-81)
     uint64_t pinned;
@@ -416,7 +442,7 @@ __device__ __forceinline__ int generate_warp(const Board& b, int turn, uint16_t*
     if (insufficient_material(b)) return 0;
     const Sets s = derive(b, turn);
     const int n_own = zc_popc64(s.own);
-    if (n_own > 32) {                                  // more pieces than lanes (only a contrived FEN): one lane does it
+    if (n_own > 32 || !s.own_king) {                   // more pieces than lanes, or no king (only a contrived FEN): one lane does it
         int n = 0;
         if (lane == 0) n = generate_cold(b, turn, out, stride);
         return __shfl_sync(0xFFFFFFFFu, n, 0);
@@ -426,8 +452,8 @@ __device__ __forceinline__ int generate_warp(const Board& b, int turn, uint16_t*
     const bool has_king = s.own_king != 0;
     const int ksq = has_king ? zc_ctz64(s.own_king) : 0;   // find_king: the first king in index order (:68-81)
     uint64_t pinned = 0;
-    const bool checked = has_king && king_danger_lines(turn, ksq, s.occ, s.own, s.e_pawn, s.e_knight, s.e_bishop | s.e_queen,
-                                                       s.e_rook | s.e_queen, s.e_king, pinned);
+    const bool checked = king_danger_lines(turn, ksq, s.occ, s.own, s.e_pawn, s.e_knight, s.e_bishop | s.e_queen,
+                                           s.e_rook | s.e_queen, s.e_king, pinned);
     uint64_t targets = 0;                              // this lane's piece may move to these squares (before the legality filter)
     int sq = 0, type = 0;
     uint32_t pawn_order = 0;                           // 4 x 6 bits: the pawn's targets in emission order (63 = none)
@@ -467,7 +493,7 @@ __device__ __forceinline__ int generate_warp(const Board& b, int turn, uint16_t*
     uint64_t work = 0;                                 // targets this lane still has to test
     int wfrom = sq;
     bool wking = type == KING;
-    if (has_king) {
+    {
         if (spread_king) {
             const uint64_t ktg = king_targets(ksq) & targets_ok;
             if (lane >= 24) {
