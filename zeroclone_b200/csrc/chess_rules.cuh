@@ -586,11 +586,10 @@ ZC_HD Board play(const Board& b, uint32_t misc, int from, int to, uint32_t& misc
     if (pc == (KING | 8) && tc - fc == 2) { put_piece(n, 5, ROOK | 8); put_piece(n, 7, 0); }
     if (pc == KING && tc - fc == -2) { put_piece(n, 59, ROOK); put_piece(n, 56, 0); }
     if (pc == (KING | 8) && tc - fc == -2) { put_piece(n, 3, ROOK | 8); put_piece(n, 0, 0); }
-    int placed = pc;
-    if (tr == 0 && pc == PAWN) placed = QUEEN;                                // :396-397
-    if (tr == 7 && pc == (PAWN | 8)) placed = QUEEN | 8;
-    put_piece(n, to, placed);
-    put_piece(n, from, 0);
+    put_piece(n, to, pc);                                                     // :393-394, in the reference's order: a move
+    put_piece(n, from, 0);                                                    // onto its own square empties the square ...
+    if (tr == 0 && pc == PAWN) put_piece(n, to, QUEEN);                       // :396-397 ... unless it "promotes" there
+    if (tr == 7 && pc == (PAWN | 8)) put_piece(n, to, QUEEN | 8);
     misc_out = m;
     return n;
 }

@@ -95,7 +95,10 @@ def check_draw(state):
 def get_legal_moves(state):
     cols = (C.c_int32 * 8)()
     n = _ffi.lib().zc_c4_legal_moves(C.byref(_c(state)), cols)
-    return {(cols[i], 0) for i in range(n)}
+    open_cols = {cols[i] for i in range(n)}
+    # inserted in ascending column order like c4_backend.py:49-50: a set's iteration order depends on its insertion
+    # history, and callers that iterate the set (engine.py's random move, the reference's tests) must see the same order
+    return {(i, 0) for i in range(COLS) if i in open_cols}
 
 
 def state_to_tensor(state):
