@@ -86,6 +86,7 @@ def f(r, k):
 
 by_fn, by_site, by_line = defaultdict(Counter), defaultdict(Counter), defaultdict(Counter)
 tot = Counter()
+hot_floor = 0.01 * max(f(r, "Instructions Executed") for r in data)     # "hot" = executed at least 1 % as often as the hottest instruction
 for r in data:
     off = int(r[0], 16) - base
     stack, _ = table.get(off, ([("?", 0)], ""))
@@ -99,7 +100,8 @@ for r in data:
             chain.append(nm)
     site = " > ".join(chain[1:4]) if len(chain) > 1 else chain[0]
     m = {"inst": f(r, "Instructions Executed"), "thread_inst": f(r, "Thread Instructions Executed"), "samples": f(r, "# Samples"),
-         "no_inst": f(r, "stall_no_inst"), "long_sb": f(r, "stall_long_sb"), "wait": f(r, "stall_wait"), "size": 1}
+         "no_inst": f(r, "stall_no_inst"), "long_sb": f(r, "stall_long_sb"), "wait": f(r, "stall_wait"), "size": 1,
+         "hot": 1 if f(r, "Instructions Executed") >= hot_floor else 0}
     for k, v in m.items():
         by_fn[fn][k] += v
         by_site[site][k] += v
@@ -108,15 +110,15 @@ for r in data:
 
 
 def show(title, d, n):
-    print(f"\n== {title} (share of executed warp instructions | lanes active | share of stall samples | no_inst share of its samples | static instructions)")
+    print(f"\n== {title} (share of executed warp instructions | lanes active | share of stall samples | no_inst share of its samples | static instructions | hot KB)")
     for name, c in sorted(d.items(), key=lambda kv: -kv[1]["inst"])[:n]:
         lanes = c["thread_inst"] / c["inst"] if c["inst"] else 0
         print(f"  {name:46s} {100 * c['inst'] / tot['inst']:5.1f} %  {lanes:4.1f}  {100 * c['samples'] / max(1, tot['samples']):5.1f} %  "
-              f"{100 * c['no_inst'] / max(1, c['samples']):5.1f} %  {int(c['size']):5d}")
+              f"{100 * c['no_inst'] / max(1, c['samples']):5.1f} %  {int(c['size']):5d}  {c['hot'] * 16 / 1024:5.1f}")
 
 
 print(f"kernel {kern}: {int(tot['size'])} static instructions ({int(tot['size']) * 16 / 1024:.0f} KB), {tot['inst']:.3e} executed, "
-      f"{tot['thread_inst'] / tot['inst']:.1f} lanes, no_inst {100 * tot['no_inst'] / max(1, tot['samples']):.1f} % of samples")
+      f"{tot['thread_inst'] / tot['inst']:.1f} lanes, no_inst {100 * tot['no_inst'] / max(1, tot['samples']):.1f} % of samples, hot code {tot['hot'] * 16 / 1024:.1f} KB")
 show("by function containing the instruction's source line", by_fn, top)
 show("by call chain below the kernel (three levels)", by_site, top)
 show("by source line", by_line, top)

@@ -649,6 +649,40 @@ __global__ void __launch_bounds__(SEARCH_BLOCK, MINB) k_search_fused(SearchParam
     __shared__ WarpPlan plans[SEARCH_BLOCK / 32];
     WarpPlan& wp = plans[threadIdx.x >> 5];
     const int lane = threadIdx.x & 31;
+#ifdef ZC_PHASE_SYNC
+    // The warps of a block start every batch together (G::kPhaseSync): a warp streams through the whole hot code once per
+    // batch, so warps in step fetch each instruction line once per block instead of once per warp.
+    if constexpr (G::kPhaseSync) {
+        const int n_batches = (p.simulations + p.batch_size - 1) / p.batch_size;
+        for (;;) {
+            int tree = 0;
+            if (lane == 0) tree = (int)atomicAdd(p.work_counter, 1u);
+            tree = __shfl_sync(FULL_MASK, tree, 0);
+            const bool have = tree < p.n_trees;
+            if (!__syncthreads_or(have)) return;
+            uint4* arena = p.arena + (uint64_t)(have ? tree : 0) * p.arena_slots;
+            uint2* path = p.path + (uint64_t)(have ? tree : 0) * p.path_cap;
+            TreeCtl ctl = p.ctl[have ? tree : 0];
+            typename G::Ctx gx = G::make_ctx(p, (blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5, lane, warp_moves[threadIdx.x >> 5]);
+            bool live = have && ctl.status == 0;
+            int done = 0;
+            for (int b = 0; b < n_batches; ++b) {
+                __syncthreads();
+                if (live) {
+                    const int B = min(p.batch_size, p.simulations - done);
+                    int d0, D;
+                    Leaf<G> leaf;
+                    if (!select_expand<G, true>(p, gx, arena, path, ctl, B, lane, wp, d0, D, leaf)) { live = false; continue; }
+                    backprop_exact<G>(arena, path, B, d0, D, lane, leaf.info, leaf.value, wp);
+                    done += B;
+                    ctl.sims_done += (uint32_t)B;
+                    live = ctl.status == 0;
+                }
+            }
+            if (have && lane == 0) p.ctl[tree] = ctl;
+        }
+    }
+#endif
     for (;;) {
         int tree = 0;
         if (lane == 0) tree = (int)atomicAdd(p.work_counter, 1u);
