@@ -5,9 +5,6 @@ import torch
 from zeroclone_b200 import _ffi
 from zeroclone_b200.search import TreeSearch
 import ctypes as C
-import os
-if os.environ.get("ZC_LIB"):      # a prebuilt variant of the library (A/B timing)
-    _ffi.LIB_PATH = os.path.abspath(os.environ["ZC_LIB"])
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 16384
 sims = int(sys.argv[2]) if len(sys.argv) > 2 else 1600

@@ -7,7 +7,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libzc_b200.so")
+LIB_PATH = os.environ.get("ZC_B200_LIB") or os.path.join(_HERE, "libzc_b200.so")     # override: A/B timing of a library variant
 
 GAME_C4, GAME_CHESS = 0, 1
 EVAL_C4_TERMINAL, EVAL_C4_POSITIONAL, EVAL_CHESS_CRUDE, EVAL_EXTERNAL, EVAL_C4_ROLLOUT = 0, 1, 2, 3, 4

@@ -7,7 +7,10 @@
 namespace zc {
 
 struct C4Game {
-    static constexpr int kMinBlocks = 7;   // resident 128-thread blocks per SM the fused search is compiled for
+#ifndef ZC_C4_MINB
+#define ZC_C4_MINB 7
+#endif
+    static constexpr int kMinBlocks = ZC_C4_MINB;   // resident 128-thread blocks per SM the fused search is compiled for
     using State = c4::State;
     // never reached: the host maps immediate_value to random for Connect Four (all move values are 0)
     ZC_D static int immediate_value_order(const uint4*, const State&, int, int, int, int j, float, uint64_t, int) { return j; }

@@ -8,7 +8,7 @@ namespace zc {
 
 struct ChessGame {
 #ifndef ZC_CHESS_MINB
-#define ZC_CHESS_MINB 8
+#define ZC_CHESS_MINB 4       // 16 warps per SM at 128 registers: +7 % over 8 blocks at 64 (spills, instruction-cache contention), A/B in profiles/
 #endif
     static constexpr int kMinBlocks = ZC_CHESS_MINB;   // resident 128-thread blocks per SM the fused search is compiled for
     using State = chess::Board;
