@@ -21,6 +21,7 @@ struct C4Game {
     static constexpr int PLANE_ELEMS = 84;  // 2 x 6 x 7 (c4_backend.py:52-61)
     static constexpr int MOVE_SCRATCH = 0;
     static constexpr bool kCheapSpine = true;   // play + legal mask are a handful of instructions
+    static constexpr bool kSmallCode = false;
     static constexpr bool kPhaseSync = false;   // the whole search fits the instruction cache (100 % hit rate measured)
     struct Ctx {};
     static constexpr int WARP_MOVES = 8;    // no staging list: moves are implied by the legal mask

@@ -16,6 +16,7 @@ struct ChessGame {
     static constexpr int FIRST_SLOTS = 32;   // header + state + first 29 edges in one warp load
     static constexpr int PLANE_ELEMS = 17 * 64;
     static constexpr bool kCheapSpine = false;  // a chain node needs a full move generation: expand level by level
+    static constexpr bool kSmallCode = true;    // butterfly loops rolled, broadcast loads instead of shuffles: the search is bound by instruction fetch
     static constexpr bool kPhaseSync = true;    // the hot code of a batch exceeds the SM's instruction cache: see k_search_fused
     static constexpr int MOVE_SCRATCH = chess::MAX_PSEUDO;   // pseudo-legal staging (>= 218 legal), multiple of 8
 
@@ -184,6 +185,7 @@ struct ChessGame {
     // ... and packed into a node's move slots by the whole warp (8 moves per slot)
     ZC_D static void store_moves_warp(Ctx& gx, uint4* dst, int k, int lane) {
         const uint4* src = reinterpret_cast<const uint4*>(gx.wmoves);
+#pragma unroll 1
         for (int i = lane; i < move_slots(k); i += 32) dst[i] = src[i];
     }
     // crude_chess_score of freshly created children (value_functions.py:49-55), one child per active lane, without

@@ -173,7 +173,7 @@ ZC_D bool descend(const SearchParams& p, const uint4* __restrict__ arena, uint2*
             const double u = uct(edge_W(ev), (int)ev.z, logN, p.c);
             if (u > best) { best = u; best_e = e; best_child = ev.w; }
         }
-#pragma unroll
+#pragma unroll (G::kSmallCode ? 1 : 5)      // rolled for chess: its fused search is bound by its instruction footprint (profiles/r2_ab_experiments.md)
         for (int d = 16; d >= 1; d >>= 1) {
             const double ob = __shfl_xor_sync(FULL_MASK, best, d);
             const int oe = __shfl_xor_sync(FULL_MASK, best_e, d);
@@ -378,6 +378,7 @@ __device__ ZC_AB_MAT_ATTR bool materialize(const SearchParams& p, typename G::Ct
     const uint32_t need = (uint32_t)node_slots<G>(k, with_priors);
     if ((uint64_t)ctl.top + need > p.arena_slots) { ctl.status = -4; return false; }
     const uint32_t base = ctl.top;
+#pragma unroll 1
     for (int t = lane; t < k; t += 32) arena[base + 1 + G::SS + t] = make_uint4(0, 0, 0, 0);   // Na = 0, Wa = 0, no child
     G::store_moves_warp(gx, arena + base + 1 + G::SS + k, k, lane);
     if (lane == 0) {
@@ -468,9 +469,7 @@ ZC_D bool expand_lazy(const SearchParams& p, typename G::Ctx& gx, uint4* __restr
         if (made >= B) break;
         // P is fully expanded and simulations remain: UCT = +inf for every fresh child, the
         // lowest move index among them wins (mcts.cpp:43,57).
-        int min_e = ei;
-#pragma unroll
-        for (int d = 16; d >= 1; d >>= 1) min_e = min(min_e, __shfl_xor_sync(FULL_MASK, min_e, d));
+        const int min_e = (int)__reduce_min_sync(FULL_MASK, (unsigned)ei);     // ei >= 0
         const unsigned who = __ballot_sync(FULL_MASK, act && ei == min_e);
         const int src = __ffs((int)who) - 1;
         if (lane == src) leaf.info |= LEAF_PATH;
