@@ -66,7 +66,7 @@ NVLINK_GBS_PER_DIR = 900.0      # NVLink 5 per GPU and direction (nominal), the 
 # run: a profiler cannot run inside the timed region).  Tower: per evaluated leaf; tree kernels: per simulation.
 NCU_TRAFFIC = {
     "tower": {"connect4": (205.4, "profiles/r2_k_value_tower_c4_ncu.txt"), "chess": (2337.7, "profiles/r2_k_value_tower_chess_ncu.txt")},
-    "tree": {"connect4": (152.4, "profiles/r2_k_search_fused_c4_ncu.txt"), "chess": (273.5, "profiles/r2_k_search_fused_chess_ncu.txt")},
+    "tree": {"connect4": (152.4, "profiles/r2_k_search_fused_c4_ncu.txt"), "chess": (91.2, "profiles/r2h_k_search_fused_chess_ncu.txt")},
 }
 
 
