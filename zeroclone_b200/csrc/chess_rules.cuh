@@ -444,6 +444,7 @@ __device__ __forceinline__ int generate_warp(const Board& b, int turn, uint16_t*
     const int n_own = zc_popc64(s.own);
     if (n_own > 32 || !s.own_king) {                   // more pieces than lanes, or no king (only a contrived FEN): one lane does it
         int n = 0;
+        if (out == nullptr) zc_layout_pad<ZC_PAD_GEN>();   // never true (zc_common.cuh: code layout)
         if (lane == 0) n = generate_cold(b, turn, out, stride);
         return __shfl_sync(0xFFFFFFFFu, n, 0);
     }

@@ -209,12 +209,13 @@ ZC_D void lowest_fresh(int policy, int k, int nexp, int m, uint64_t nkey, int la
 // child, ...) are computed by the whole warp redundantly, then ALL batch_size leaves are created
 // in ONE lane-parallel step (lane i = pending[i]) instead of one step per chain level.
 // ---------------------------------------------------------------------------------------------
-template <class G, bool kBuiltinEval>
+template <class G, bool kBuiltinEval, bool KEYED = true>
 ZC_D bool expand_spine(const SearchParams& p, typename G::Ctx& gx, uint4* __restrict__ arena, uint2* __restrict__ path,
                        TreeCtl& ctl, int B, int lane, uint32_t P, const uint4& hdr, const typename G::State& Pst,
                        int d0, WarpPlan& wp, int& D_out, Leaf<G>& leaf) {
     const uint64_t tkey = p.seed ^ ((uint64_t)ctl.tree_id << 32);
-    const bool keyed = p.policy >= 2;                          // only the randomised policies order moves by a node key,
+    const int policy = KEYED ? p.policy : (p.policy & 1);      // KEYED = false: first / last only, the randomised orders are compiled out
+    const bool keyed = policy >= 2;                            // only the randomised policies order moves by a node key,
     const bool drawn = p.evaluator == ZC_EVAL_C4_ROLLOUT;      // only the rollout evaluator draws random numbers
     typename G::State Sg = Pst;
     uint32_t Mg = hdr_misc(hdr);
@@ -252,7 +253,7 @@ ZC_D bool expand_spine(const SearchParams& p, typename G::Ctx& gx, uint4* __rest
         // the node is fully expanded and simulations remain: every fresh child has UCT = +inf, the lowest
         // move index among them wins (mcts.cpp:43,57)
         int e_star, j_star;
-        lowest_fresh(p.policy, kg, nexpg, m, keyed ? rng_mix(tkey ^ G::state_key(Sg, Mg)) : 0ull, lane, e_star, j_star);
+        lowest_fresh(policy, kg, nexpg, m, keyed ? rng_mix(tkey ^ G::state_key(Sg, Mg)) : 0ull, lane, e_star, j_star);
         const int next_lane = made - m + j_star;
         if (g == 0) P_e = e_star;
         else if (lane == spine_lane) my_spine_e = e_star;
@@ -277,7 +278,7 @@ ZC_D bool expand_spine(const SearchParams& p, typename G::Ctx& gx, uint4* __rest
     uint32_t cmisc = myPm;
     double val = 0.0;
     if (is_leaf) {
-        ei = expansion_order(p.policy, myk, mynexp + myj, keyed ? rng_mix(tkey ^ G::state_key(myP, myPm)) : 0ull);
+        ei = expansion_order(policy, myk, mynexp + myj, keyed ? rng_mix(tkey ^ G::state_key(myP, myPm)) : 0ull);
         cs = G::child(myP, myPm, nullptr, myk, ei, cmisc);
         ck = G::count_moves(gx, cs, cmisc);
         if (kBuiltinEval)
@@ -371,6 +372,7 @@ __device__ ZC_AB_MAT_ATTR bool materialize(const SearchParams& p, typename G::Ct
     const int k = G::moves_warp(gx, st, misc, lane);
     k_out = k;
     if (k == 0) {                                            // move-less node: same footprint as the stub
+        if (p.n_trees < 0) zc_layout_pad<ZC_PAD_MAT>();          // never true (zc_common.cuh: code layout)
         if (lane == 0) arena[node].y = 0u;
         __syncwarp();
         return true;
@@ -393,7 +395,7 @@ __device__ ZC_AB_MAT_ATTR bool materialize(const SearchParams& p, typename G::Ct
     return true;
 }
 
-template <class G, bool kBuiltinEval>
+template <class G, bool kBuiltinEval, bool KEYED = true>
 ZC_D bool expand_lazy(const SearchParams& p, typename G::Ctx& gx, uint4* __restrict__ arena, uint2* __restrict__ path,
                       TreeCtl& ctl, int B, int lane, uint32_t P, const uint4& hdr, const typename G::State& st,
                       int d0, WarpPlan& wp, int& D_out, Leaf<G>& leaf) {
@@ -413,6 +415,7 @@ ZC_D bool expand_lazy(const SearchParams& p, typename G::Ctx& gx, uint4* __restr
     while (made < B) {
         if (lane == 0) wp.off[g] = made;
         if (Pk == 0) {                       // move-less node: select() returns it again and again (:59)
+            if (p.n_trees < 0) zc_layout_pad<ZC_PAD_MAIN>();     // never true (zc_common.cuh: code layout)
             if (lane >= made && lane < B) {
                 leaf.info = LEAF_SELF | (uint32_t)D;
                 leaf.st = Pst;
@@ -429,17 +432,20 @@ ZC_D bool expand_lazy(const SearchParams& p, typename G::Ctx& gx, uint4* __restr
         const int m = min(Pk - Pnexp, B - made);
         const int j = lane - made;
         const bool act = j >= 0 && j < m;
-        const uint64_t nkey = p.policy >= 2 ? rng_mix(tkey ^ G::state_key(Pst, Pmisc)) : 0ull;      // only the randomised policies are keyed
+        const int policy = KEYED ? p.policy : (p.policy & 1);     // KEYED = false: first / last only, the randomised orders are compiled out
+        const uint64_t nkey = policy >= 2 ? rng_mix(tkey ^ G::state_key(Pst, Pmisc)) : 0ull;      // only the randomised policies are keyed
         int ei = 0x7FFFFFFF;
         typename G::State cs = Pst;
         uint32_t cmisc = 0;
         int ei_iv = 0;
         // random: the node's keyed uniformly random order; immediate_value: the warp replays the node's pick process (uniform
         // among the untried moves within policy_freedom of the best untried capture value)
-        if (p.policy == 2) ei_iv = G::random_order(gx, Pk, Pnexp, m, j, nkey, lane);
-        else if (p.policy == 3) ei_iv = G::immediate_value_order(arena + P, Pst, Pk, Pnexp, m, j, p.policy_freedom, nkey, lane);
+        if constexpr (KEYED) {
+            if (policy == 2) ei_iv = G::random_order(gx, Pk, Pnexp, m, j, nkey, lane);
+            else if (policy == 3) ei_iv = G::immediate_value_order(arena + P, Pst, Pk, Pnexp, m, j, p.policy_freedom, nkey, lane);
+        }
         if (act) {
-            ei = p.policy >= 2 ? ei_iv : expansion_order(p.policy, Pk, Pnexp + j, nkey);
+            ei = policy >= 2 ? ei_iv : expansion_order(policy, Pk, Pnexp + j, nkey);
             cs = G::child(Pst, Pmisc, arena + P, Pk, ei, cmisc);
         }
         const int total = m * (1 + G::SS);
@@ -498,7 +504,7 @@ ZC_D bool expand_lazy(const SearchParams& p, typename G::Ctx& gx, uint4* __restr
 
 // select + expand one batch for one tree.  Leaves end up one per lane (lane i = pending[i]).
 // Returns false if the arena overflowed (tree is then flagged and abandoned).
-template <class G, bool kBuiltinEval>
+template <class G, bool kBuiltinEval, bool KEYED = true>
 ZC_D bool select_expand(const SearchParams& p, typename G::Ctx& gx, uint4* __restrict__ arena, uint2* __restrict__ path,
                         TreeCtl& ctl, int B, int lane, WarpPlan& wp, int& d0_out, int& D_out, Leaf<G>& leaf) {
     uint32_t P;
@@ -507,8 +513,8 @@ ZC_D bool select_expand(const SearchParams& p, typename G::Ctx& gx, uint4* __res
     typename G::State st;
     if (!descend<G>(p, arena, path, ctl, lane, P, d0, hdr, st)) return false;
     d0_out = d0;
-    if constexpr (G::kCheapSpine) return expand_spine<G, kBuiltinEval>(p, gx, arena, path, ctl, B, lane, P, hdr, st, d0, wp, D_out, leaf);
-    else return expand_lazy<G, kBuiltinEval>(p, gx, arena, path, ctl, B, lane, P, hdr, st, d0, wp, D_out, leaf);
+    if constexpr (G::kCheapSpine) return expand_spine<G, kBuiltinEval, KEYED>(p, gx, arena, path, ctl, B, lane, P, hdr, st, d0, wp, D_out, leaf);
+    else return expand_lazy<G, kBuiltinEval, KEYED>(p, gx, arena, path, ctl, B, lane, P, hdr, st, d0, wp, D_out, leaf);
 }
 
 // leaves that are not on the chain: their node and their edge see exactly one backprop
@@ -642,7 +648,9 @@ constexpr int SEARCH_BLOCK = ZC_SEARCH_BLOCK;
 
 // Fused persistent search with a built-in evaluator: the whole simulation loop of get_move
 // (mcts.cpp:129-149) for every tree.  Warps pull tree indices from a global counter.
-template <class G, int MINB = G::kMinBlocks>
+// KEYED = false serves the deterministic expansion orders (first / last) without the code of the randomised ones: the hot code
+// of a kernel competes for the SM's instruction cache, and what is not there cannot push it apart.
+template <class G, bool KEYED = true, int MINB = G::kMinBlocks>
 __global__ void __launch_bounds__(SEARCH_BLOCK, MINB) k_search_fused(SearchParams p) {
     __shared__ __align__(16) uint16_t warp_moves[SEARCH_BLOCK / 32][G::WARP_MOVES];   // chess: the warp generator's move list
     __shared__ WarpPlan plans[SEARCH_BLOCK / 32];
@@ -671,7 +679,7 @@ __global__ void __launch_bounds__(SEARCH_BLOCK, MINB) k_search_fused(SearchParam
                     const int B = min(p.batch_size, p.simulations - done);
                     int d0, D;
                     Leaf<G> leaf;
-                    if (!select_expand<G, true>(p, gx, arena, path, ctl, B, lane, wp, d0, D, leaf)) { live = false; continue; }
+                    if (!select_expand<G, true, KEYED>(p, gx, arena, path, ctl, B, lane, wp, d0, D, leaf)) { live = false; continue; }
                     backprop_exact<G>(arena, path, B, d0, D, lane, leaf.info, leaf.value, wp);
                     done += B;
                     ctl.sims_done += (uint32_t)B;
@@ -695,7 +703,7 @@ __global__ void __launch_bounds__(SEARCH_BLOCK, MINB) k_search_fused(SearchParam
             const int B = min(p.batch_size, p.simulations - done);
             int d0, D;
             Leaf<G> leaf;
-            if (!select_expand<G, true>(p, gx, arena, path, ctl, B, lane, wp, d0, D, leaf)) break;
+            if (!select_expand<G, true, KEYED>(p, gx, arena, path, ctl, B, lane, wp, d0, D, leaf)) break;
             backprop_exact<G>(arena, path, B, d0, D, lane, leaf.info, leaf.value, wp);   // built-in values are exactly summable
             done += B;
             ctl.sims_done += (uint32_t)B;

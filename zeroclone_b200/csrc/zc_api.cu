@@ -71,7 +71,7 @@ struct zc_search {
     int32_t* adv_err_dev = nullptr;     // {flags, first offending tree}
     int64_t bytes = 0;
     int64_t launches = 0;
-    int fused_grid = 0;
+    int fused_grid = 0, fused_grid_det = 0;      // grids of k_search_fused<G, true> / <G, false>
     int order_version = 0;
     // split-phase state
     int sp_left = 0, sp_batch = 0, sp_policy = 0, sp_selected = 0;
@@ -369,11 +369,14 @@ extern "C" int zc_search_create(int game, int device, int max_trees, int max_sim
         volatile double x = (double)i;
         lt[i] = std::log(x);
     }
-    int occ = 0, sms = 0;
+    int occ = 0, occ_det = 0, sms = 0;      // resident blocks per SM of the two instantiations (randomised / deterministic orders)
     e = cudaMemcpy(h->log_tab, lt.data(), lt.size() * sizeof(double), cudaMemcpyHostToDevice);
     if (e == cudaSuccess)
-        e = game == ZC_GAME_C4 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_search_fused<C4Game>, SEARCH_BLOCK, 0)
-                               : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_search_fused<ChessGame>, SEARCH_BLOCK, 0);
+        e = game == ZC_GAME_C4 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_search_fused<C4Game, true>, SEARCH_BLOCK, 0)
+                               : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_search_fused<ChessGame, true>, SEARCH_BLOCK, 0);
+    if (e == cudaSuccess)
+        e = game == ZC_GAME_C4 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_det, k_search_fused<C4Game, false>, SEARCH_BLOCK, 0)
+                               : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_det, k_search_fused<ChessGame, false>, SEARCH_BLOCK, 0);
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_res_ready, cudaEventDisableTiming);
@@ -391,8 +394,9 @@ extern "C" int zc_search_create(int game, int device, int max_trees, int max_sim
         return fail(ZC_ECUDA, msg);
     }
     h->fused_grid = occ * sms;
+    h->fused_grid_det = occ_det * sms;
     if (game == ZC_GAME_CHESS) {
-        const size_t warps = (size_t)std::max(max_trees, h->fused_grid * (SEARCH_BLOCK / 32));
+        const size_t warps = (size_t)std::max(max_trees, std::max(h->fused_grid, h->fused_grid_det) * (SEARCH_BLOCK / 32));
         const size_t sb = warps * 32 * ChessGame::MOVE_SCRATCH * sizeof(uint16_t);
         h->bytes += (int64_t)sb;
         cudaError_t se = cudaMalloc((void**)&h->scratch, sb);
@@ -538,8 +542,13 @@ extern "C" int zc_search_run(zc_search* h, int simulations, double c, int batch_
         CUDA_TRY(cudaGetLastError());
         return ZC_OK;
     }
-    const int grid = blocks_needed < h->fused_grid ? blocks_needed : h->fused_grid;
-    ZC_DISPATCH(h->game, k_search_fused<G><<<grid, SEARCH_BLOCK, 0, st>>>(p));
+    if (policy >= ZC_POLICY_RANDOM) {
+        const int grid = blocks_needed < h->fused_grid ? blocks_needed : h->fused_grid;
+        ZC_DISPATCH(h->game, (k_search_fused<G, true><<<grid, SEARCH_BLOCK, 0, st>>>(p)));
+    } else {                                 // first / last: the instantiation without the randomised orders' code
+        const int grid = blocks_needed < h->fused_grid_det ? blocks_needed : h->fused_grid_det;
+        ZC_DISPATCH(h->game, (k_search_fused<G, false><<<grid, SEARCH_BLOCK, 0, st>>>(p)));
+    }
     h->launches++;
     CUDA_TRY(cudaGetLastError());
     return ZC_OK;
