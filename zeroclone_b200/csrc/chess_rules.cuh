@@ -379,7 +379,10 @@ ZC_HD int generate(const Board& b, int turn, uint16_t* out, int stride = 1) {
 
 #ifdef __CUDACC__
 // out of line: reached only for a contrived position with more than 32 pieces of one colour
-__device__ __noinline__ int generate_cold(const Board& b, int turn, uint16_t* out, int stride) { return generate(b, turn, out, stride); }
+__device__ __noinline__ int generate_cold(const Board& b, int turn, uint16_t* out, int stride) {
+    if (out == nullptr) zc_layout_pad<ZC_PAD_COLD>();      // never true (zc_common.cuh: code layout); this function sits between the hot ones
+    return generate(b, turn, out, stride);
+}
 
 // The king of the side to move: is it attacked, and which own pieces are PINNED to it (the first piece met from the king
 // along a line is own and the next one beyond it is an enemy slider of that line's kind)?  Line form of king_danger().

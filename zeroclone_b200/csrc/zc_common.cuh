@@ -31,6 +31,9 @@
 #ifndef ZC_PAD_GEN
 #define ZC_PAD_GEN 0
 #endif
+#ifndef ZC_PAD_COLD
+#define ZC_PAD_COLD 40
+#endif
 template <int N>
 __device__ __forceinline__ void zc_layout_pad() {
 #pragma unroll
