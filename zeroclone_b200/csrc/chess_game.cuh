@@ -16,8 +16,8 @@ struct ChessGame {
     static constexpr int FIRST_SLOTS = 32;   // header + state + first 29 edges in one warp load
     static constexpr int PLANE_ELEMS = 17 * 64;
     static constexpr bool kCheapSpine = false;  // a chain node needs a full move generation: expand level by level
-    static constexpr bool kSmallCode = true;    // butterfly loops rolled, broadcast loads instead of shuffles: the search is bound by instruction fetch
-    static constexpr bool kPhaseSync = true;    // the hot code of a batch exceeds the SM's instruction cache: see k_search_fused
+    static constexpr bool kSmallCode = true;    // the descent's argmax butterfly stays rolled: the search is bound by instruction fetch
+    static constexpr bool kPhaseSync = true;    // with -DZC_PHASE_SYNC (off: measured slower) the warps of a block start every batch together
     static constexpr int MOVE_SCRATCH = chess::MAX_PSEUDO;   // pseudo-legal staging (>= 218 legal), multiple of 8
 
     static constexpr int WARP_MOVES = chess::MAX_PSEUDO;   // entries of the per-warp staging list in shared memory
