@@ -218,3 +218,19 @@ def test_shipped_chess_value_config_at_its_own_size():
         st = eng.last_search_stats(i)
         assert int(st["visits"].sum()) == sims and st["best"] == int(st["visits"].argmax())
         assert len(eng.history[i].states) == 2
+
+
+def test_timing_check_script_like_the_reference(tmp_path):
+    """scripts/timing_check.py (reference: scripts/timing_check.py:15-58): same flags, same five printed lines"""
+    import subprocess
+    import sys
+    repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for cfg, extra in (("configs/chess_value.yaml", []), ("configs/crude_chess.yaml", ["--trees", "64"])):
+        out = subprocess.run([sys.executable, "scripts/timing_check.py", "-c", cfg, "--sims", "64", "--batch", "32", "--loops", "3", *extra],
+                             cwd=repo, env=dict(os.environ, PYTHONPATH=repo), capture_output=True, text=True, timeout=600)
+        assert out.returncode == 0, out.stderr[-2000:]
+        lines = out.stdout.strip().splitlines()
+        assert lines[0] == "--- get_move timing (3 runs) ---" and lines[1] == "simulations : 64" and lines[2] == "batch size  : 32"
+        assert lines[3].startswith("mean  time  : ") and lines[4].startswith("median time : ")
+        if extra:
+            assert lines[5].startswith("batched     : 64 trees in ")
