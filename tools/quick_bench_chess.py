@@ -8,6 +8,7 @@ import ctypes as C
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 16384
 sims = int(sys.argv[2]) if len(sys.argv) > 2 else 1600
+policy = {"first": _ffi.POLICY_FIRST, "random": _ffi.POLICY_RANDOM, "immediate_value": _ffi.POLICY_IMMEDIATE_VALUE}[sys.argv[3] if len(sys.argv) > 3 else "first"]
 L = _ffi.lib()
 s = _ffi.ChessState()
 L.zc_chess_init_state(C.byref(s))
@@ -31,7 +32,7 @@ for r in range(3):
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
     a.record()
-    ts.run(sims, 1.4, 32, _ffi.EVAL_CHESS_CRUDE, _ffi.POLICY_FIRST)
+    ts.run(sims, 1.4, 32, _ffi.EVAL_CHESS_CRUDE, policy)
     b.record()
     torch.cuda.synchronize()
     ms = a.elapsed_time(b)
