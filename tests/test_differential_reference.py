@@ -112,3 +112,32 @@ def test_connect4_on_hand_made_boards(ref_c4):
         for col in range(7):                                # any column, full ones included (the reference then only flips the turn)
             na, nr = c4.play_move(a, (col, 0)), ref_c4.play_move(r, (col, 0))
             assert [list(x) for x in na.board] == [list(x) for x in nr.board] and na.turn == nr.turn, (rows, col)
+
+
+def test_chess_random_games_every_function_every_ply(ref_chess):
+    """Whole random games played in lockstep by both backends: at every ply the legal move lists (order and capture values),
+    check_win, check_draw (incl. the fifty-ply counter and the repetition test on the accumulated histories), the state after
+    the move and the network planes must be the same.  Also from odd starting boards and with castling flags cleared."""
+    from zeroclone_b200.games.chess import chess_backend as cb
+    rng = np.random.default_rng(2024)
+    starts = [(list(cb.create_init_state().board), 0)] * 40 + odd_boards(60, seed=9)
+    plies = games_over = 0
+    for gi, (b, turn) in enumerate(starts):
+        flags = [True] * 4 if gi < 40 else [bool(x) for x in rng.integers(0, 2, 4)]
+        a = mine_state(cb, b, turn, 0, flags)
+        r = ref_chess.State(list(b), turn, 0, *flags, [], [])
+        for ply in range(160):
+            ma, mr = cb.get_legal_moves(a), ref_chess.get_legal_moves(r)
+            assert [(tuple(m[0]), float(m[1])) for m in ma] == [(tuple(m[0]), float(m[1])) for m in mr], (gi, ply)
+            wa, wr = cb.check_win(a), ref_chess.check_win(r)
+            da, dr = cb.check_draw(a), ref_chess.check_draw(r)
+            assert (wa, da) == (wr, dr), (gi, ply)
+            assert np.array_equal(cb.state_to_tensor(a), np.asarray(ref_chess.state_to_tensor(r))), (gi, ply)
+            if wa or da or not ma:
+                games_over += 1
+                break
+            k = int(rng.integers(len(ma)))
+            a, r = cb.play_move(a, ma[k]), ref_chess.play_move(r, mr[k])
+            assert same_state(a, r), (gi, ply)
+            plies += 1
+    assert plies > 3000 and games_over > 20, (plies, games_over)
