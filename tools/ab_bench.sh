@@ -1,5 +1,5 @@
 #!/bin/bash
-# A/B of prebuilt library variants (variants/*.so) on the benchmark's own workloads: usage  tools/ab_minb.sh <workload> <variant>...
+# A/B of prebuilt library variants (variants/*.so) on the benchmark's own workloads: usage  tools/ab_bench.sh <workload> <variant>...
 export PYTHONPATH=$PWD
 w=$1; shift
 for v in "$@"; do
