@@ -113,3 +113,31 @@ def test_chess_immediate_value_policy_expansion_order(freedom):
         if sims == 30:
             check_sampled(ts, n, sims, 1000.0, sample=4)
     assert len(seen_sets) > 10, "trees of one position must not all expand the same moves (device RNG per tree)"
+
+
+@pytest.mark.parametrize("freedom,crit", [(0.0, 10.83), (2.0, 24.32), (3.0, 80.08)])
+def test_chess_immediate_value_first_pick_is_uniform_over_the_candidates(freedom, crit):
+    """random.choice([a for a in moves if a[1] >= best - policy_freedom]) (policy_functions.py:14-17): the FIRST expansion of a
+    root picks uniformly among exactly those moves.  20 000 trees on one position (Kiwipete: 46 moves in the reference's rules, captures worth 1 and 3);
+    chi-square at p = 0.001 for the candidate count of each freedom (2, 8 and 46 candidates: df 1, 7, 45)."""
+    from zeroclone_b200.games.chess import chess_backend as cb
+    root = cb.state_from_fen("r3k2r/p1ppqpb1/bn2pnp1/3PN3/1p2P3/2N2Q1p/PPPBBPPP/R3K2R w KQkq - 0 1")
+    moves = cb.get_legal_moves(root)
+    vals = np.array([m[1] for m in moves])
+    cand = np.nonzero(vals >= vals.max() - freedom)[0]
+    n = 20000
+    roots = np.zeros(n, dtype=_ffi.CHESS_STATE_DTYPE)
+    roots[:] = cb.pack_state(root)
+    ts = TreeSearch(_ffi.GAME_CHESS, n, 32)
+    ts.set_roots(roots)
+    ts.set_policy_freedom(freedom)
+    ts.run(1, 1.4, 1, _ffi.EVAL_CHESS_CRUDE, _ffi.POLICY_IMMEDIATE_VALUE, seed=23)
+    out = ts.results()
+    first = out["visits"][:, :len(moves)].argmax(axis=1)
+    assert (out["visits"].sum(axis=1) == 1).all()
+    counts = np.bincount(first, minlength=len(moves)).astype(np.float64)
+    assert counts[np.setdiff1d(np.arange(len(moves)), cand)].sum() == 0          # never a move outside the candidate set
+    e = n / len(cand)
+    chi2 = float(((counts[cand] - e) ** 2 / e).sum())
+    print(f"freedom {freedom}: {len(cand)} candidates of {len(moves)} moves, chi2 {chi2:.1f} (critical {crit})")
+    assert chi2 < crit
