@@ -141,3 +141,57 @@ def test_chess_random_games_every_function_every_ply(ref_chess):
             assert same_state(a, r), (gi, ply)
             plies += 1
     assert plies > 3000 and games_over > 20, (plies, games_over)
+
+
+def test_rest_wire_format_equals_the_stock_serializer():
+    """server/main.py:14-36 `serialize_state` is the REST wire format: what the UNMODIFIED function makes of the reference's
+    states must be what this repo's server makes of this repo's states (same keys, same values, same JSON)."""
+    import json
+    import subprocess
+    import sys
+    repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    fens = ["rnbqkbnr/pppppppp/8/8/8/8/PPPPPPPP/RNBQKBNR w KQkq - 0 1", "r3k2r/p1ppqpb1/bn2pnp1/3PN3/1p2P3/2N2Q1p/PPPBBPPP/R3K2R b Kq - 7 1",
+            "8/8/8/1k6/8/8/4K3/5B2 w - - 49 1"]
+    script = r'''
+import json, sys, importlib
+sys.path.insert(0, REPO)
+if STOCK:
+    from oracle import ref_harness as rh
+    s = rh.stock(need_torch=True)
+    chess, c4 = s.chess, s.c4
+    import importlib.util, os
+    spec = importlib.util.spec_from_file_location("_stock_server_main", os.path.join(rh.pyref_dir(), "server", "main.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)            # imports the stock engine.engine (sys.path: pyref first)
+    ser = mod.serialize_state
+    assert sys.modules["engine.engine"].__file__.startswith(rh.pyref_dir())
+else:
+    from zeroclone_b200.games.chess import chess_backend as chess
+    from zeroclone_b200.games.connect4 import c4_backend as c4
+    from server.main import serialize_state as ser
+out = []
+for fen in FENS:
+    st = chess.state_from_fen(fen)
+    out.append(ser(st))
+    for k in (0, 3, 5):
+        mv = chess.get_legal_moves(st)
+        if mv:
+            st = chess.play_move(st, mv[k % len(mv)])
+            out.append(ser(st))
+st = c4.create_init_state()
+out.append(ser(st))
+for col in (3, 3, 4, 0, 6):
+    st = c4.play_move(st, (col, 0))
+    out.append(ser(st))
+print("WIRE " + json.dumps(out, sort_keys=True))
+'''
+    got = []
+    for stock in (True, False):
+        code = f"REPO, STOCK, FENS = {repo!r}, {stock!r}, {fens!r}\n" + script
+        run = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600, cwd=repo if not stock else "/tmp",
+                             env=dict(os.environ, CUDA_VISIBLE_DEVICES=""))
+        assert run.returncode == 0, run.stderr[-3000:]
+        got.append(json.loads([l for l in run.stdout.splitlines() if l.startswith("WIRE ")][-1][5:]))
+    assert len(got[0]) == len(got[1]) > 12
+    for a, b in zip(got[1], got[0]):
+        assert a == b, (a, b)
